@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — assignments/sec of the scheduler-tick hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --steps K --warmup W    # restated reference tick on the host CPU
+
+One "step" = one scheduler tick over one batch of synthetic input: BASELINE.json configs[1]
+(1M independent ready tasks x 256 workers x 4 resource kinds, one fractional; Q=16 request classes,
+Zipf(1.1) class mix, 8 priority levels), mode M1 of SURVEY.md §8(d): capacity >= demand, so every ready
+task is assigned in that one tick and value = tasks / tick time.
+
+  value     device-resident: the ready set already sits in HBM; the timed region holds K ticks on K
+            different contexts (252 MB of distinct task tables > the 126 MB L2, so no step re-reads a
+            warm table), each tick = upload of the worker state + count_k + solve_k + emit_k.
+  e2e       the same tick through the public C ABI with HOST buffers: hqs_ready_push (H2D of task,
+            class, priority arrays from pinned memory) + hqs_tick (D2H of the 8-byte assignments and the
+            free vectors) inside the timed region.
+  roofline  emit_k (the kernel with the most algorithmic HBM traffic) timed with CUDA events on the
+            context stream, against MEASURED_PEAKS.json; per-kernel times are in "kernels".
+  cpu_baseline  the oracle (restated reference tick, HiGHS 1.12.0) on a bounded sample of the same
+            workload, single-threaded like the reference (Rc<RefCell<Core>>).
+
+N > 1 GPUs: the task table is block-sharded by handle over the ranks; the only exchange is an NCCL
+all-gather of the per-group count vectors (16 KB) and the replicated deterministic solve (weak scaling:
+1M tasks per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_TASKS = 1_000_000
+N_WORKERS = 256
+N_CLASSES = 16
+FREE_SCALE = 1024
+METRIC = "assignments/sec on 1M ready tasks x 256 workers x 4 resource kinds"
+WORKLOAD = "cfg2-M1: 1M independent tasks, 256 workers, R=4 (gpus fractional), Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int = 0) -> None:
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop = threading.Event()
+
+    def run(self) -> None:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(n_tasks: int, seed: int, n_workers: int = N_WORKERS, free_scale: int = FREE_SCALE):
+    import parity as P
+    return P.make_independent(n_tasks, n_workers, N_CLASSES, seed=seed, free_scale=free_scale)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host CPU
+# ---------------------------------------------------------------------------------------------------
+def oracle_step(sample: int, seed: int):
+    """One M1 tick of the restated reference on a `sample`-task cut of the workload.  Returns
+    (assignments, seconds) — queue construction is outside the timed region, like the HBM-resident
+    ready set of the CUDA arm."""
+    import parity as P
+    wl = make_workload(sample, seed)
+    core = P.oracle_core(wl)
+    core.scheduler_state.config.proactive_filling_max = 0
+    t0 = time.perf_counter()
+    mapping = core.schedule_mapping(0.0, **P.ORACLE_FAST)
+    dt = time.perf_counter() - t0
+    return mapping.n_assigned(), dt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.ref_sample
+    for i in range(args.warmup):
+        oracle_step(sample, 100 + i)
+    n_tot, t_tot = 0, 0.0
+    for i in range(args.steps):
+        n, dt = oracle_step(sample, i)
+        n_tot += n
+        t_tot += dt
+    value = n_tot / t_tot if t_tot > 0 else 0.0
+    desc = {"value": value, "unit": "assignments/s", "cores": 1, "kind": "port",
+            "sample": f"{sample}-task cut of the workload per step (same class mix, 256 workers, one M1 tick); "
+                      f"oracle = restated reference tick (Python + HiGHS 1.12.0 via scipy, 1 % MIP gap, 2 s cap); "
+                      f"host has {os.cpu_count()} cores, 1 used (the reference tick is single-threaded)"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_sample_tasks": sample},
+        "cpu_baseline": desc,
+        "e2e": {"value": value, "unit": "assignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------
+def run_cuda(args) -> None:
+    import torch
+    import torch.distributed as dist
+    import parity as P
+    from hyperqueue_b200 import _lib as L, priority_from_user
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    K, Wm = args.steps, args.warmup
+    n_ctx = K + Wm
+
+    # one stream shared by every context so the ticks serialise and torch events time them
+    stream = torch.cuda.Stream(device=dev)
+    wl = make_workload(N_TASKS, seed=0)        # one class table / worker pool for every rank
+    if rank:
+        wl.task_class = np.roll(wl.task_class, rank * 104729)
+        wl.task_user_priority = np.roll(wl.task_user_priority, rank * 15485863 % N_TASKS)
+    prio = priority_from_user(wl.task_user_priority)
+    handles = np.arange(N_TASKS, dtype=np.uint32)
+    scheds = []
+    for i in range(n_ctx):
+        s = P.gpu_scheduler(wl, add_tasks=False, device=local_rank)
+        s._sync_classes()
+        s._check(s._lib.hqs_set_stream(s._ctx, C.c_void_p(stream.cuda_stream)))
+        # distinct device tables; rotate the class/priority arrays so the tables differ
+        s.add_ready_tasks(handles, np.roll(wl.task_class, i * 7919), np.roll(prio, i * 7919))
+        scheds.append(s)
+    torch.cuda.synchronize()
+
+    workers = scheds[0]._worker_structs(0.0)
+    free = np.ascontiguousarray(wl.worker_free)
+    total = np.ascontiguousarray(wl.worker_total)
+    lib = scheds[0]._lib
+
+    def launch(s, counts=None):
+        s._check(lib.hqs_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
+
+    def sharded_tick(s, bufs):
+        # count locally, all-gather the count vectors, replicated solve, local emit
+        cnt, gathered = bufs
+        ng = C.c_uint32(0)
+        s._check(lib.hqs_shard_count(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None,
+                                     C.c_void_p(cnt.data_ptr()), cnt.numel(), C.byref(ng)))
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, cnt)
+            g2 = gathered.view(world, -1)
+            allc = g2.sum(0, dtype=torch.int64).to(torch.int32)
+            before = g2[:rank].sum(0, dtype=torch.int64).to(torch.int32) if rank else torch.zeros_like(cnt)
+        s._sh = (allc, before)
+        s._check(lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(allc.data_ptr()), C.c_void_p(before.data_ptr()), N_TASKS))
+
+    bufs = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            bufs = (torch.zeros(L.HQS_MAX_GROUPS, dtype=torch.int32, device=dev),
+                    torch.zeros(L.HQS_MAX_GROUPS * world, dtype=torch.int32, device=dev))
+
+    def step(s):
+        if world > 1:
+            sharded_tick(s, bufs)
+        else:
+            launch(s)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed region: exactly K steps, events on the launching stream -----------
+    for i in range(Wm):
+        step(scheds[i])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(K):
+        step(scheds[Wm + i])
+    ev1.record(stream)
+    barrier()
+    t_host = time.perf_counter() - t_host0
+    ms_total = ev0.elapsed_time(ev1)
+    launches_timed = 3 * K
+    # every step must have assigned every task
+    out_n = C.c_uint32(0)
+    tmp_out = np.zeros(N_TASKS, dtype=L.assignment_dtype)
+    for i in range(K):
+        s = scheds[Wm + i]
+        s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(tmp_out), C.byref(out_n), None))
+        if world == 1:
+            assert out_n.value == N_TASKS, f"step {i}: {out_n.value} of {N_TASKS} tasks assigned"
+    n_done_local = N_TASKS if world == 1 else int(out_n.value)
+
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        n_all = torch.tensor([n_done_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_all)
+        n_per_step = int(n_all.item())
+    else:
+        n_per_step = N_TASKS
+    ms_per_step = ms_total / K
+    value = n_per_step / (ms_per_step / 1000.0)
+
+    # ---- per-kernel device times (profiled pass, same workload, re-armed tables) ----------------
+    kernels = {}
+    if world == 1:
+        acc = np.zeros(4)
+        reps = 0
+        for i in range(K):
+            s = scheds[Wm + i]
+            s._check(lib.hqs_ready_rearm(s._ctx))
+            s._check(lib.hqs_set_profile(s._ctx, 1))
+        torch.cuda.synchronize()
+        for i in range(K):
+            s = scheds[Wm + i]
+            launch(s)
+            torch.cuda.synchronize()
+            ms = (C.c_float * 4)()
+            s._check(lib.hqs_get_kernel_ms(s._ctx, ms))
+            acc += np.array(list(ms))
+            reps += 1
+            s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(tmp_out), C.byref(out_n), None))
+        acc /= max(reps, 1)
+        st = scheds[Wm].stats()
+        peak, peak_src = _peaks()
+        bytes_count = 4.0 * N_TASKS
+        bytes_emit = (4.0 + 8.0 + 4.0) * N_TASKS          # key read + assignment write + key write-back
+        kernels = {
+            "count_k": {"ms": acc[0], "algorithmic_bytes": bytes_count, "GBps": bytes_count / acc[0] / 1e6},
+            "solve_k": {"ms": acc[1], "groups": st["n_groups"], "note": "one CTA, latency-bound sequential first-fit; no HBM stream"},
+            "emit_k": {"ms": acc[2], "algorithmic_bytes": bytes_emit, "GBps": bytes_emit / acc[2] / 1e6},
+            "sum_ms": acc[3],
+        }
+        achieved = bytes_emit / acc[2] / 1e6
+        roofline = {"bound": "hbm", "kernel": "emit_k", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_task": 16, "note": "interned classes: 4 B key read + 8 B assignment + 4 B key write-back per task "
+                                                  "(SURVEY §8(d) budgets 36 B/task for un-interned per-task amounts)",
+                    "tick_frac_of_hbm": ((4.0 + 16.0) * N_TASKS / (ms_per_step / 1000.0) / 1e9) / peak}
+    else:
+        roofline = None
+
+    # ---- e2e: host buffers through the public C ABI -----------------------------------------------
+    e2e = None
+    if rank == 0:
+        s = scheds[0]
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        h_handles, h_cls, h_prio = pin(handles), pin(np.ascontiguousarray(wl.task_class)), pin(prio)
+        out = torch.empty(N_TASKS * 8, dtype=torch.uint8).pin_memory().numpy().view(L.assignment_dtype)
+        free_after = np.zeros_like(free)
+        n_e2e = max(3, min(K, 10))
+
+        def e2e_step():
+            s._check(lib.hqs_ready_push(s._ctx, N_TASKS, L.ptr(h_handles), L.ptr(h_cls), L.ptr(h_prio)))
+            s._check(lib.hqs_tick(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS,
+                                  L.ptr(out), C.byref(out_n), L.ptr(free_after)))
+            assert out_n.value == N_TASKS
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": N_TASKS / dt, "unit": "assignments/s", "ms_per_step": dt * 1000.0, "steps": n_e2e,
+               "h2d_bytes_per_step": int(N_TASKS * 16 + free.nbytes + total.nbytes + workers.nbytes),
+               "d2h_bytes_per_step": int(N_TASKS * 8 + free.nbytes + 16), "n_gpus": 1,
+               "note": "hqs_ready_push + hqs_tick with pinned host buffers, host clock around synchronised calls"}
+    clocks = sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n, dt = oracle_step(args.ref_sample, 0)
+        cpu = {"value": n / dt, "unit": "assignments/s", "cores": 1, "kind": "port",
+               "sample": f"one M1 tick of the restated reference (Python + HiGHS 1.12.0) on a {args.ref_sample}-task cut "
+                         f"of the workload, {dt:.1f} s; host has {os.cpu_count()} cores, 1 used"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tasks_per_gpu": N_TASKS, "l2_policy": "each timed step runs on a different "
+                       "12 MB task table (K+W tables, 21 x 12 MB > 126 MB L2): inputs larger than L2",
+                       "host_wall_ms_per_step": 1000.0 * t_host / K},
+            "gpu_launches": launches_timed, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu,
+        }))
+    for s in scheds:
+        s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

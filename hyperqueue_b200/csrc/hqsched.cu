@@ -1,0 +1,1361 @@
+// hqsched.cu — B200 (sm_100a) task->worker assignment solver behind the C ABI of include/hqsched.h.
+//
+// Replaces, for the single-node hot path of HyperQueue's tako scheduler tick (v0.26.0):
+//   create_task_batches        crates/tako/src/internal/scheduler/batches.rs:42-181   (priority histogram)
+//   run_scheduling_solver      crates/tako/src/internal/scheduler/solver.rs:16-461    (who gets how many)
+//   create_task_mapping        crates/tako/src/internal/scheduler/mapping.rs:23-154   (which task goes where)
+//   TaskQueues                 crates/tako/src/internal/scheduler/taskqueue.rs        (ready set, device resident)
+//   task_finished readiness    crates/tako/src/internal/server/reactor.rs:500-580     (DAG mode)
+// It is NOT a port: the reference solves a MILP over (worker, class, variant) counts with HiGHS; this
+// library runs a deterministic priority-ordered first-fit over the same aggregation, with the per-task
+// work (histogram, stable ranking, emission) as streaming kernels over an SoA task table in HBM.
+// See DESIGN.md for the data layout, the kernels and their rooflines.
+//
+// Device data (all SoA, indexed by dense task handle h):
+//   key[h]   u32  bit31 READY | bit30 DONE (assigned by a tick) | bit29 VALID | level(15) | class(14)
+//   prio[h]  u64  tako Priority (only read when the level table changes)
+//   deps[h]  u32  unfinished dependencies (DAG mode), cons_off/cons: CSR of consumers
+// One tick = 3 kernels on one stream:
+//   count_k : per-chunk histogram of ready tasks by group g = level*Q + class   (HBM streaming, 4 B/task)
+//   solve_k : CTA 0: sequential first-fit over non-empty groups, one thread per worker;
+//             CTAs 1..: exclusive scan of the per-chunk histograms over chunks (runs concurrently)
+//   emit_k  : stable rank of every ready task inside its group, rank -> (worker, variant) through
+//             the solver's count segments, compact write of 8-byte assignments, READY -> DONE
+#include "../../include/hqsched.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+constexpr u32 KEY_READY = 1u << 31;
+constexpr u32 KEY_DONE = 1u << 30;
+constexpr u32 KEY_VALID = 1u << 29;
+constexpr u32 KEY_LEVEL_SHIFT = 14;
+constexpr u32 KEY_LEVEL_MASK = 0x7FFFu;
+constexpr u32 KEY_CLASS_MASK = 0x3FFFu;
+
+constexpr u32 EMIT_WARPS = 8;             // warps per CTA in count_k / emit_k
+constexpr u32 EMIT_THREADS = EMIT_WARPS * 32;
+constexpr u32 CHUNK_ALIGN = EMIT_THREADS; // chunk size granularity (every warp gets whole 32-task rows)
+constexpr u32 SEG_CAP = 1u << 20;         // (group, worker, variant) count segments per tick
+constexpr u32 NEWPRIO_CAP = 4096;
+
+__device__ __forceinline__ u32 key_level(u32 k) { return (k >> KEY_LEVEL_SHIFT) & KEY_LEVEL_MASK; }
+__device__ __forceinline__ u32 key_class(u32 k) { return k & KEY_CLASS_MASK; }
+
+// Per-group result of the solver, read by emit_k with one 16-byte load.
+struct __align__(16) GroupOut {
+    u32 k;        // tasks of this group assigned this tick (global count in sharded mode)
+    u32 out_off;  // offset of the group's first assignment in the (local) output
+    u32 seg_lo;   // first count segment
+    u32 seg_n;    // number of count segments
+};
+
+// Device-side variant: dense amounts for the context's R resources.
+struct DevVariant {
+    u64 amount[HQS_MAX_RESOURCES];
+    u64 min_time_ms;
+    u32 all_mask;
+    u32 used_mask;  // bit r: amount[r] != 0 or all_mask bit r
+};
+struct DevClass {
+    u32 n_variants;
+    u32 pad;
+    DevVariant v[HQS_MAX_VARIANTS];
+};
+
+struct TickHeaderOut {
+    u32 n_assigned;  // local assignments
+    u32 n_groups;
+    u32 n_segments;
+    u32 error;       // 1 = segment overflow
+};
+
+// ------------------------------------------------------------------------------------------------
+// level lookup: levels[] sorted by DESCENDING priority.  exact mode: index of the entry equal to p
+// (or ~0u if absent); coarse mode: levels[i] is the lowest priority of bucket i, index of the first
+// bucket whose bound <= p (clamped to the last bucket).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 find_level(const u64* __restrict__ levels, u32 n_levels, u64 p, bool coarse) {
+    u32 lo = 0, hi = n_levels;  // first index with levels[i] <= p
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (__ldg(levels + mid) <= p) hi = mid; else lo = mid + 1;
+    }
+    if (coarse) return lo < n_levels ? lo : n_levels - 1;
+    if (lo < n_levels && __ldg(levels + lo) == p) return lo;
+    return ~0u;
+}
+
+// ready-set maintenance ---------------------------------------------------------------------------
+__global__ void push_k(u32 n, const u32* __restrict__ task, const u32* __restrict__ cls,
+                       const u64* __restrict__ prio_in, u32* __restrict__ key, u64* __restrict__ prio,
+                       const u64* __restrict__ levels, u32 n_levels, int coarse, u32* __restrict__ newcnt,
+                       u64* __restrict__ newprio) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const u32 h = live ? task[i] : 0u;
+    const u64 p = live ? prio_in[i] : 0ull;
+    u32 lvl = (live && n_levels) ? find_level(levels, n_levels, p, coarse != 0) : ~0u;
+    // unknown priority: report it to the host (one atomic per warp), key it provisionally to level 0;
+    // relevel_k fixes every key once the host has merged the new priority
+    const bool fresh = live && lvl == ~0u;
+    const u32 fm = __ballot_sync(0xffffffffu, fresh);
+    if (fm) {
+        const u32 lane = threadIdx.x & 31;
+        u32 slot0 = 0;
+        if (lane == (u32)(__ffs(fm) - 1)) slot0 = atomicAdd(newcnt, (u32)__popc(fm));
+        slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(fm) - 1);
+        if (fresh) {
+            const u32 slot = slot0 + __popc(fm & ((1u << lane) - 1));
+            if (slot < NEWPRIO_CAP) newprio[slot] = p;
+            lvl = 0;
+        }
+    }
+    if (!live) return;
+    prio[h] = p;
+    key[h] = KEY_READY | KEY_VALID | (lvl << KEY_LEVEL_SHIFT) | (cls[i] & KEY_CLASS_MASK);
+}
+
+__global__ void relevel_k(u32 n_handles, u32* __restrict__ key, const u64* __restrict__ prio,
+                          const u64* __restrict__ levels, u32 n_levels, int coarse) {
+    u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_handles) return;
+    u32 k = key[h];
+    if (!(k & KEY_VALID)) return;
+    u32 lvl = find_level(levels, n_levels, prio[h], coarse != 0);
+    if (lvl == ~0u) lvl = 0;
+    key[h] = (k & ~(KEY_LEVEL_MASK << KEY_LEVEL_SHIFT)) | (lvl << KEY_LEVEL_SHIFT);
+}
+
+__global__ void remove_k(u32 n, const u32* __restrict__ task, u32* __restrict__ key, u32 n_handles) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 h = task[i];
+    if (h < n_handles) key[h] &= ~KEY_READY;
+}
+
+__global__ void rearm_k(u32 n_handles, u32* __restrict__ key) {
+    u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_handles) return;
+    u32 k = key[h];
+    if (k & KEY_DONE) key[h] = (k & ~KEY_DONE) | KEY_READY;
+}
+
+__global__ void dag_init_k(u32 n, const u32* __restrict__ cls, const u64* __restrict__ prio,
+                           const u32* __restrict__ deps, u32* __restrict__ key,
+                           const u64* __restrict__ levels, u32 n_levels, int coarse) {
+    u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    u32 lvl = find_level(levels, n_levels, prio[h], coarse != 0);
+    if (lvl == ~0u) lvl = 0;
+    key[h] = KEY_VALID | (deps[h] == 0 ? KEY_READY : 0u) | (lvl << KEY_LEVEL_SHIFT) | (cls[h] & KEY_CLASS_MASK);
+}
+
+// task_finished (reactor.rs:545-571): one thread per (finished task, consumer) pair would need a
+// segmented layout; out-degree is small (<= 8 in the benchmark DAG), so one thread per finished task.
+__global__ void finished_k(u32 n, const u32* __restrict__ task, const u32* __restrict__ cons_off,
+                           const u32* __restrict__ cons, u32* __restrict__ deps, u32* __restrict__ key,
+                           u32* __restrict__ n_new) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 made = 0;
+    if (i < n) {
+        u32 t = task[i];
+        u32 lo = cons_off[t], hi = cons_off[t + 1];
+        for (u32 e = lo; e < hi; ++e) {
+            u32 c = cons[e];
+            if (atomicSub(&deps[c], 1u) == 1u) {  // decrease_unfinished_deps() hit zero
+                atomicOr(&key[c], KEY_READY);
+                ++made;
+            }
+        }
+    }
+    made = __reduce_add_sync(0xffffffffu, made);
+    if ((threadIdx.x & 31) == 0 && made) atomicAdd(n_new, made);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: count_k — histogram of ready tasks per group for one chunk of the task table.
+// HBM traffic: 4 B read per table slot.  smem: G u32 counters.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EMIT_THREADS)
+count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32* __restrict__ table,
+        u32* __restrict__ total) {
+    extern __shared__ u32 s_hist[];
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) s_hist[g] = 0;
+    __syncthreads();
+    const u32 base = blockIdx.x * chunk;
+    const u32 end = min(base + chunk, n_handles);
+    const u32 lane = threadIdx.x & 31;
+    // chunk and base are multiples of 256 => 16-byte aligned uint4 loads; a ragged tail is scalar.
+    const u32 vec_end = base + ((end - base) & ~3u);
+    // the loop is uniform across the CTA (the warp collectives below need all 32 lanes)
+    for (u32 rowb = base; rowb < end; rowb += blockDim.x * 4) {
+        const u32 i = rowb + threadIdx.x * 4;
+        u32 k[4];
+        if (i + 4 <= vec_end) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(key + i));
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) k[j] = (i + j < end) ? __ldg(key + i + j) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ready = (k[j] & KEY_READY) != 0;
+            const u32 g = key_level(k[j]) * Q + key_class(k[j]);
+            // warp-aggregated shared-memory increment (few hot groups under a skewed class mix)
+            const u32 act = __ballot_sync(0xffffffffu, ready);
+            if (ready) {
+                const u32 peers = __match_any_sync(act, g);
+                if ((u32)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[g], (u32)__popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    u32* row = table + (size_t)blockIdx.x * G;
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+        const u32 v = s_hist[g];
+        row[g] = v;
+        if (v) atomicAdd(&total[g], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: solve_k.  CTA 0: first-fit solver.  CTAs >= 1: exclusive scan of table[][g] over chunks.
+// ------------------------------------------------------------------------------------------------
+struct SolveArgs {
+    // tick input (device copy of the host staging buffer)
+    const u64* free_rw;    // [W][R]
+    const u64* total_rw;   // [W][R]
+    const u64* rem_time;   // [W]
+    const u32* order;      // [Q] class ids in processing order inside one priority level
+    const uint8_t* blocked;  // [W][Q] bytes (bit v) or nullptr
+    const DevClass* classes;
+    u32 W, Q, L, R, G;
+    // counts
+    u32* total_local;      // [G] counts of this rank (zeroed here for the next tick)
+    const u32* total_all;  // [G] counts summed over ranks (== total_local when not sharded)
+    const u32* before;     // [G] counts of lower ranks, or nullptr
+    // outputs
+    GroupOut* gout;        // [G]
+    u32* seg_cum;          // [SEG_CAP] inclusive end rank of the segment inside its group
+    u32* seg_wv;           // [SEG_CAP] worker | variant << 16
+    u64* free_after;       // [W][R]
+    TickHeaderOut* hdr;
+    u32* glist;            // [G] scratch: non-empty groups in processing order
+    // scan part
+    u32* table;            // [P][G]
+    u32 P;
+};
+
+template <int RT>
+__device__ void solve_body(const SolveArgs& a) {
+    __shared__ u64 s_wsum[32];
+    __shared__ u32 s_nlist;
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31, warp = tid >> 5;
+    const u32 nwarps = blockDim.x >> 5;
+    const bool has_worker = tid < a.W;
+
+    u64 fr[RT], tot[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        fr[r] = (has_worker && r < (int)a.R) ? a.free_rw[(size_t)tid * a.R + r] : 0;
+        tot[r] = (has_worker && r < (int)a.R) ? a.total_rw[(size_t)tid * a.R + r] : 0;
+    }
+    const u64 rem_time = has_worker ? a.rem_time[tid] : 0;
+
+    // ---- compact the non-empty groups, in processing order: level asc (= priority desc), then the
+    //      tick's class order
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    const u32 n_pos = a.L * a.Q;
+    for (u32 base = 0; base < n_pos; base += blockDim.x) {
+        const u32 pos = base + tid;
+        u32 g = 0;
+        bool nz = false;
+        if (pos < n_pos) {
+            const u32 lvl = pos / a.Q, j = pos - lvl * a.Q;
+            g = lvl * a.Q + a.order[j];
+            nz = a.total_all[g] != 0;
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        u32 off = s_nlist;
+        for (u32 w2 = 0; w2 < warp; ++w2) off += (u32)s_wsum[w2];
+        if (nz) a.glist[off + __popc(bal & ((1u << lane) - 1))] = g;
+        __syncthreads();
+        if (tid == 0) {
+            u32 t = 0;
+            for (u32 w2 = 0; w2 < nwarps; ++w2) t += (u32)s_wsum[w2];
+            s_nlist += t;
+        }
+        __syncthreads();
+    }
+    const u32 n_list = s_nlist;
+
+    u32 seg_base = 0;    // uniform across the CTA
+    u32 out_base = 0;    // uniform: local output offset
+    bool seg_overflow = false;
+
+    for (u32 li = 0; li < n_list; ++li) {
+        const u32 g = a.glist[li];
+        const u32 c = g % a.Q;
+        const u32 n_all = a.total_all[g];
+        const DevClass* cl = a.classes + c;
+        const u32 nv = cl->n_variants;
+        u32 remaining = n_all;
+        const u32 seg_lo = seg_base;
+        const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
+
+        for (u32 v = 0; v < nv && remaining > 0; ++v) {
+            const DevVariant* dv = &cl->v[v];
+            const u32 all_mask = dv->all_mask;
+            const u32 used_mask = dv->used_mask;
+            // ---- how many tasks of (c, v) fit on my worker now
+            u64 cnt = 0;
+            if (has_worker && !((blk >> v) & 1) && (rem_time == HQS_TIME_INF || dv->min_time_ms <= rem_time)) {
+                cnt = remaining;
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    if (!((used_mask >> r) & 1)) continue;
+                    if ((all_mask >> r) & 1) {
+                        // `All`: feasible with >= 1 fraction (request.rs:34-36) but consumes the total
+                        // (solver.rs:120-124) => at most one task, only on an untouched resource
+                        const u64 q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
+                        cnt = cnt < q ? cnt : q;
+                    } else if (fr[r] != HQS_AMOUNT_MAX) {
+                        const u64 q = fr[r] / dv->amount[r];
+                        cnt = cnt < q ? cnt : q;
+                    }
+                }
+            }
+            // ---- block-wide scan of (cnt, cnt>0) packed in one u64: low 42 bits count, high bits flag
+            u64 x = cnt | (cnt ? (1ull << 42) : 0ull);
+            u64 inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int)lane >= d) inc += y;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            // every warp scans the warp totals redundantly (no second barrier needed for the offsets)
+            u64 wt = lane < nwarps ? s_wsum[lane] : 0;
+            u64 winc = wt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 y = __shfl_up_sync(0xffffffffu, winc, d);
+                if ((int)lane >= d) winc += y;
+            }
+            const u64 block_total = __shfl_sync(0xffffffffu, winc, 31);
+            const u64 warp_off = warp ? __shfl_sync(0xffffffffu, winc, warp - 1) : 0;
+            const u64 exc = warp_off + inc - x;
+            const u64 exc_cnt = exc & ((1ull << 42) - 1);
+            const u32 exc_flag = (u32)(exc >> 42);
+            u32 take = 0;
+            if (cnt && exc_cnt < remaining) {
+                const u64 room = remaining - exc_cnt;
+                take = (u32)(cnt < room ? cnt : room);
+            }
+            const u32 done_before = n_all - remaining;
+            if (take) {
+                const u32 si = seg_base + exc_flag;
+                if (si < SEG_CAP) {
+                    a.seg_cum[si] = done_before + (u32)exc_cnt + take;
+                    a.seg_wv[si] = tid | (v << 16);
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    if (!((used_mask >> r) & 1)) continue;
+                    if ((all_mask >> r) & 1) fr[r] = 0;                              // workerload.rs:162
+                    else if (fr[r] != HQS_AMOUNT_MAX) fr[r] -= (u64)take * dv->amount[r];
+                }
+            }
+            const u32 n_takers = (u32)__syncthreads_count(take != 0);   // also fences s_wsum reuse
+            const u64 tot_cnt = block_total & ((1ull << 42) - 1);
+            const u32 taken = (u32)(tot_cnt < remaining ? tot_cnt : remaining);
+            remaining -= taken;
+            seg_base += n_takers;
+            if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+        }
+
+        const u32 k = n_all - remaining;
+        // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
+        const u32 bef = a.before ? a.before[g] : 0;
+        const u32 loc = a.total_local[g];
+        u32 k_loc = k > bef ? k - bef : 0;
+        k_loc = k_loc < loc ? k_loc : loc;
+        if (tid == 0) {
+            GroupOut go;
+            go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_base - seg_lo;
+            a.gout[g] = go;
+        }
+        out_base += k_loc;
+    }
+
+    // ---- epilogue: header, free vectors after the tick, reset the local counters for the next tick
+    if (has_worker) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (r < (int)a.R) a.free_after[(size_t)tid * a.R + r] = fr[r];
+    }
+    if (tid == 0) {
+        a.hdr->n_assigned = out_base;
+        a.hdr->n_groups = n_list;
+        a.hdr->n_segments = seg_base;
+        a.hdr->error = seg_overflow ? 1u : 0u;
+    }
+    __syncthreads();
+    for (u32 g = tid; g < a.G; g += blockDim.x) a.total_local[g] = 0;
+}
+
+template <int RT>
+__global__ void __launch_bounds__(1024) solve_k(SolveArgs a) {
+    if (blockIdx.x == 0) {
+        solve_body<RT>(a);
+        return;
+    }
+    // exclusive scan over chunks, one thread per group column; rows are contiguous => coalesced
+    const u32 g = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    if (g >= a.G) return;
+    u32 run = 0;
+    u32* col = a.table + g;
+    u32 b = 0;
+    for (; b + 4 <= a.P; b += 4) {   // 4 independent loads in flight
+        const u32 v0 = col[(size_t)(b + 0) * a.G], v1 = col[(size_t)(b + 1) * a.G];
+        const u32 v2 = col[(size_t)(b + 2) * a.G], v3 = col[(size_t)(b + 3) * a.G];
+        col[(size_t)(b + 0) * a.G] = run; run += v0;
+        col[(size_t)(b + 1) * a.G] = run; run += v1;
+        col[(size_t)(b + 2) * a.G] = run; run += v2;
+        col[(size_t)(b + 3) * a.G] = run; run += v3;
+    }
+    for (; b < a.P; ++b) {
+        const u32 v = col[(size_t)b * a.G];
+        col[(size_t)b * a.G] = run;
+        run += v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: emit_k — stable (handle-ordered) rank of every ready task inside its group, rank -> placement.
+// Each warp owns a contiguous sub-chunk; per-warp group counters live in shared memory:
+//   s_cnt[w][g]  first pass: tasks of group g in warp w's sub-chunk; then turned into the global rank
+//                at which warp w's first task of group g starts; second pass: running counter.
+// HBM traffic: 4 B read per table slot (second read hits L1/L2), 8 B written per assignment, 4 B key
+// write-back per assignment.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, const u32* __restrict__ table,
+       const u32* __restrict__ before, const GroupOut* __restrict__ gout, const u32* __restrict__ seg_cum,
+       const u32* __restrict__ seg_wv, hqs_assignment* __restrict__ out, u32 out_cap) {
+    extern __shared__ u32 s_cnt[];   // [EMIT_WARPS][G]
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 i = threadIdx.x; i < EMIT_WARPS * G; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+
+    const u32 base = blockIdx.x * chunk;
+    const u32 end = min(base + chunk, n_handles);
+    const u32 sub = chunk / EMIT_WARPS;              // multiple of 32
+    const u32 wbeg = base + warp * sub;
+    const u32 wend = min(wbeg + sub, end);
+    u32* mycnt = s_cnt + warp * G;
+
+    // pass 1: per-warp counts
+    for (u32 i = wbeg + lane; i < wbeg + sub; i += 32) {
+        const u32 k = (i < wend) ? __ldg(key + i) : 0u;
+        const bool ready = (k & KEY_READY) != 0;
+        const u32 g = key_level(k) * Q + key_class(k);
+        const u32 act = __ballot_sync(0xffffffffu, ready);
+        if (ready) {
+            const u32 peers = __match_any_sync(act, g);
+            if ((u32)(__ffs(peers) - 1) == lane) mycnt[g] += __popc(peers);
+        }
+        if (i - lane + 32 >= wend) break;   // uniform: whole row past the end
+    }
+    __syncthreads();
+    // turn counts into starting ranks: rank0(w, g) = before[g] + table[b][g] + sum_{w' < w} cnt[w'][g]
+    const u32* row = table + (size_t)blockIdx.x * G;
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+        u32 run = row[g];
+#pragma unroll
+        for (u32 w2 = 0; w2 < EMIT_WARPS; ++w2) {
+            const u32 c = s_cnt[w2 * G + g];
+            s_cnt[w2 * G + g] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+
+    // pass 2: rank and emit
+    for (u32 i = wbeg + lane; i < wbeg + sub; i += 32) {
+        const u32 k = (i < wend) ? key[i] : 0u;
+        const bool ready = (k & KEY_READY) != 0;
+        const u32 g = key_level(k) * Q + key_class(k);
+        const u32 act = __ballot_sync(0xffffffffu, ready);
+        if (ready) {
+            const u32 peers = __match_any_sync(act, g);
+            const u32 leader = __ffs(peers) - 1;
+            u32 r0 = 0;
+            if (leader == lane) {
+                r0 = mycnt[g];
+                mycnt[g] = r0 + __popc(peers);
+            }
+            r0 = __shfl_sync(peers, r0, leader);
+            const u32 r_loc = r0 + __popc(peers & ((1u << lane) - 1));   // rank among this rank's tasks
+            const u32 bef = before ? __ldg(before + g) : 0u;
+            const GroupOut go = gout[g];
+            if (r_loc + bef < go.k) {
+                const u32 r = r_loc + bef;                                // global rank in the group
+                // first segment whose inclusive end rank exceeds r
+                u32 lo = go.seg_lo, hi = go.seg_lo + go.seg_n;
+                while (lo < hi) {
+                    const u32 mid = (lo + hi) >> 1;
+                    if (__ldg(seg_cum + mid) > r) hi = mid; else lo = mid + 1;
+                }
+                const u32 wv = __ldg(seg_wv + lo);
+                const u32 oi = go.out_off + r_loc;
+                if (oi < out_cap) {
+                    hqs_assignment asg;
+                    asg.task = i;
+                    asg.worker = (uint16_t)(wv & 0xFFFFu);
+                    asg.variant = (uint8_t)(wv >> 16);
+                    asg.kind = 0;
+                    out[oi] = asg;
+                }
+                key[i] = (k & ~KEY_READY) | KEY_DONE;                     // Waiting -> Assigned
+            }
+        }
+        if (i - lane + 32 >= wend) break;
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct hqs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    u32 R = 0;
+    std::string err;
+    // classes
+    u32 Q = 0;
+    std::vector<hqs_class> classes;
+    DevClass* d_classes = nullptr;
+    u32 d_classes_cap = 0;
+    // priority levels (descending)
+    std::vector<u64> levels;      // exact distinct priorities seen, descending
+    std::vector<u64> dev_levels;  // what the device uses (== levels, or bucket bounds when coarsened)
+    bool coarse = false;
+    u64* d_levels = nullptr;
+    u32 d_levels_cap = 0;
+    // task table
+    u32 n_handles = 0, cap_handles = 0;
+    u32* d_key = nullptr;
+    u64* d_prio = nullptr;
+    u32* d_deps = nullptr;
+    u32* d_cons_off = nullptr;
+    u32* d_cons = nullptr;
+    bool dag = false;
+    // push staging (device)
+    u32* d_push_task = nullptr; u32* d_push_cls = nullptr; u64* d_push_prio = nullptr;
+    u32 push_cap = 0;
+    u32* d_newcnt = nullptr; u64* d_newprio = nullptr;
+    // tick buffers
+    u32 sm_count = 148;
+    u32 G_cap = 0, P_cap = 0;
+    u32* d_table = nullptr;
+    u32* d_total = nullptr;
+    GroupOut* d_gout = nullptr;
+    u32* d_glist = nullptr;
+    u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr;
+    hqs_assignment* d_out = nullptr; u32 out_cap_dev = 0;
+    TickHeaderOut* d_hdr = nullptr;
+    u64* d_free_after = nullptr;
+    unsigned char* d_tickin = nullptr; size_t tickin_cap = 0;
+    unsigned char* h_tickin = nullptr;  // pinned
+    unsigned char* h_hdr = nullptr;     // pinned: TickHeaderOut + free_after
+    size_t h_hdr_cap = 0;
+    u32* h_small = nullptr;             // pinned scratch (counters)
+    // last tick
+    u32 last_W = 0, last_G = 0, last_L = 0;
+    bool tick_pending = false;
+    bool own_stream = true;
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    hqs_stats stats{};
+};
+
+namespace {
+
+int fail(hqs_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, HQS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename T>
+int dev_realloc(hqs_ctx* ctx, T** p, size_t old_n, size_t new_n, bool keep, bool zero_new) {
+    T* q = nullptr;
+    CU(cudaMalloc(&q, new_n * sizeof(T)));
+    if (zero_new) CU(cudaMemsetAsync(q, 0, new_n * sizeof(T), ctx->stream));
+    if (keep && *p && old_n) CU(cudaMemcpyAsync(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (*p) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(*p));
+    }
+    *p = q;
+    return HQS_OK;
+}
+
+int ensure_handles(hqs_ctx* ctx, u32 need) {
+    if (need <= ctx->cap_handles) return HQS_OK;
+    u32 cap = std::max<u32>(need, std::max<u32>(ctx->cap_handles * 2, 1u << 16));
+    cap = (cap + 1023u) & ~1023u;
+    int rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_key, ctx->cap_handles, cap, true, true))) return rc;
+    if ((rc = dev_realloc(ctx, &ctx->d_prio, ctx->cap_handles, cap, true, true))) return rc;
+    ctx->cap_handles = cap;
+    return HQS_OK;
+}
+
+// (Re)builds the device level table from ctx->levels, coarsening when L * Q exceeds HQS_MAX_GROUPS.
+int upload_levels(hqs_ctx* ctx) {
+    const u32 q = std::max<u32>(ctx->Q, 1);
+    const u32 max_levels = std::max<u32>(1, HQS_MAX_GROUPS / q);
+    const u32 L = (u32)ctx->levels.size();
+    ctx->dev_levels.clear();
+    if (L <= max_levels) {
+        ctx->dev_levels = ctx->levels;
+        ctx->coarse = false;
+    } else {
+        // merge adjacent levels into max_levels buckets; entry i = lowest priority of bucket i
+        ctx->coarse = true;
+        for (u32 b = 0; b < max_levels; ++b) {
+            const u64 last = ((u64)(b + 1) * L) / max_levels - 1;
+            ctx->dev_levels.push_back(ctx->levels[last]);
+        }
+        ctx->dev_levels.back() = 0;  // the last bucket takes everything below
+    }
+    const u32 n = (u32)ctx->dev_levels.size();
+    if (n > ctx->d_levels_cap) {
+        if (ctx->d_levels) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(ctx->d_levels)); ctx->d_levels = nullptr; }
+        ctx->d_levels_cap = std::max<u32>(n * 2, 64);
+        CU(cudaMalloc(&ctx->d_levels, ctx->d_levels_cap * sizeof(u64)));
+    }
+    if (n) {
+        // pageable source: the copy is staged by the runtime before the call returns
+        CU(cudaMemcpyAsync(ctx->d_levels, ctx->dev_levels.data(), n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stats.coarsened = ctx->coarse ? 1 : 0;
+    return HQS_OK;
+}
+
+int relevel_all(hqs_ctx* ctx) {
+    if (!ctx->n_handles || ctx->dev_levels.empty()) return HQS_OK;
+    relevel_k<<<(ctx->n_handles + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->n_handles, ctx->d_key, ctx->d_prio, ctx->d_levels, (u32)ctx->dev_levels.size(), ctx->coarse ? 1 : 0);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    return HQS_OK;
+}
+
+// merges new distinct priorities into the level set; returns true if the set changed
+bool merge_levels(hqs_ctx* ctx, std::vector<u64>& fresh) {
+    std::sort(fresh.begin(), fresh.end(), std::greater<u64>());
+    fresh.erase(std::unique(fresh.begin(), fresh.end()), fresh.end());
+    std::vector<u64> merged;
+    merged.reserve(ctx->levels.size() + fresh.size());
+    std::merge(ctx->levels.begin(), ctx->levels.end(), fresh.begin(), fresh.end(), std::back_inserter(merged),
+               std::greater<u64>());
+    merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+    const bool changed = merged.size() != ctx->levels.size();
+    ctx->levels.swap(merged);
+    return changed;
+}
+
+void distinct_priorities(const u64* p, u32 n, std::vector<u64>& out) {
+    // small open-addressing set with a last-value fast path; distinct priorities are few
+    std::vector<u64> slots(1024, 0);
+    std::vector<unsigned char> used(1024, 0);
+    size_t count = 0;
+    u64 last = n ? ~p[0] : 0;
+    for (u32 i = 0; i < n; ++i) {
+        const u64 v = p[i];
+        if (v == last) continue;
+        last = v;
+        if ((count + 1) * 2 > slots.size()) {
+            std::vector<u64> ns(slots.size() * 4, 0);
+            std::vector<unsigned char> nu(slots.size() * 4, 0);
+            for (size_t s = 0; s < slots.size(); ++s)
+                if (used[s]) {
+                    size_t h = (slots[s] * 0x9E3779B97F4A7C15ull) >> 20 & (ns.size() - 1);
+                    while (nu[h]) h = (h + 1) & (ns.size() - 1);
+                    ns[h] = slots[s]; nu[h] = 1;
+                }
+            slots.swap(ns); used.swap(nu);
+        }
+        size_t h = (v * 0x9E3779B97F4A7C15ull) >> 20 & (slots.size() - 1);
+        while (used[h] && slots[h] != v) h = (h + 1) & (slots.size() - 1);
+        if (!used[h]) { used[h] = 1; slots[h] = v; ++count; }
+    }
+    for (size_t s = 0; s < slots.size(); ++s) if (used[s]) out.push_back(slots[s]);
+}
+
+int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
+    if (G > ctx->G_cap || P > ctx->P_cap) {
+        const u32 ng = std::max(G, ctx->G_cap), np = std::max(P, ctx->P_cap);
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_table) CU(cudaFree(ctx->d_table));
+        CU(cudaMalloc(&ctx->d_table, (size_t)ng * np * sizeof(u32)));
+        if (ng > ctx->G_cap) {
+            if (ctx->d_total) CU(cudaFree(ctx->d_total));
+            if (ctx->d_gout) CU(cudaFree(ctx->d_gout));
+            if (ctx->d_glist) CU(cudaFree(ctx->d_glist));
+            CU(cudaMalloc(&ctx->d_total, ng * sizeof(u32)));
+            CU(cudaMemsetAsync(ctx->d_total, 0, ng * sizeof(u32), ctx->stream));
+            CU(cudaMalloc(&ctx->d_gout, ng * sizeof(GroupOut)));
+            CU(cudaMemsetAsync(ctx->d_gout, 0, ng * sizeof(GroupOut), ctx->stream));
+            CU(cudaMalloc(&ctx->d_glist, ng * sizeof(u32)));
+        }
+        ctx->G_cap = ng; ctx->P_cap = np;
+    }
+    if (!ctx->d_seg_cum) {
+        CU(cudaMalloc(&ctx->d_seg_cum, SEG_CAP * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_seg_wv, SEG_CAP * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_hdr, sizeof(TickHeaderOut)));
+        CU(cudaMalloc(&ctx->d_free_after, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
+    }
+    if (out_cap > ctx->out_cap_dev) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_out) CU(cudaFree(ctx->d_out));
+        ctx->out_cap_dev = std::max<u32>(out_cap, 1024);
+        CU(cudaMalloc(&ctx->d_out, (size_t)ctx->out_cap_dev * sizeof(hqs_assignment)));
+    }
+    (void)W;
+    return HQS_OK;
+}
+
+struct TickLayout {
+    size_t off_free, off_total, off_rem, off_order, off_blocked, bytes;
+};
+
+TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
+    TickLayout l;
+    size_t o = 0;
+    l.off_free = o; o += (size_t)W * R * 8;
+    l.off_total = o; o += (size_t)W * R * 8;
+    l.off_rem = o; o += (size_t)W * 8;
+    l.off_order = o; o += (size_t)Q * 4;
+    o = (o + 15) & ~size_t(15);
+    l.off_blocked = o; if (blocked) o += (size_t)W * Q;
+    l.bytes = (o + 15) & ~size_t(15);
+    return l;
+}
+
+// processing order of classes inside one priority level: descending objective weight of one task,
+// the greedy analogue of the MILP coefficient of create_sn_var (solver.rs:520-549):
+//   weight * sum_r amount_r / S_r,   S_r = sum over workers of free[r] (MAX counts as one unit)
+void class_order(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total_rw, u32* order) {
+    const u32 R = ctx->R, Q = ctx->Q;
+    double S[HQS_MAX_RESOURCES], T[HQS_MAX_RESOURCES];
+    for (u32 r = 0; r < R; ++r) { S[r] = 0; T[r] = 0; }
+    for (u32 w = 0; w < W; ++w)
+        for (u32 r = 0; r < R; ++r) {
+            const u64 f = free_rw[(size_t)w * R + r];
+            S[r] += f == HQS_AMOUNT_MAX ? 1.0 : (double)f / 10000.0;
+            const u64 t = total_rw[(size_t)w * R + r];
+            T[r] += t == HQS_AMOUNT_MAX ? 1.0 : (double)t / 10000.0;
+        }
+    std::vector<std::pair<double, u32>> sc(Q);
+    for (u32 c = 0; c < Q; ++c) {
+        double best = 0;
+        const hqs_class& cl = ctx->classes[c];
+        for (u32 v = 0; v < cl.n_variants; ++v) {
+            double s = 0;
+            for (u32 r = 0; r < R; ++r) {
+                if (S[r] < 1e-6) continue;
+                if ((cl.variants[v].all_mask >> r) & 1) s += (T[r] / std::max<u32>(W, 1)) / S[r];
+                else s += ((double)cl.variants[v].amount[r] / 10000.0) / S[r];
+            }
+            s *= (double)cl.variants[v].weight / 10000.0;
+            best = std::max(best, s);
+        }
+        sc[c] = {best, c};
+    }
+    std::stable_sort(sc.begin(), sc.end(), [](const std::pair<double, u32>& a, const std::pair<double, u32>& b) {
+        return a.first > b.first;
+    });
+    for (u32 c = 0; c < Q; ++c) order[c] = sc[c].second;
+}
+
+struct TickGeom { u32 G, L, P, chunk; };
+
+TickGeom tick_geom(const hqs_ctx* ctx) {
+    TickGeom t;
+    t.L = std::max<u32>((u32)ctx->dev_levels.size(), 1);
+    t.G = t.L * std::max<u32>(ctx->Q, 1);
+    // shared memory of emit_k: EMIT_WARPS * G * 4 B; two CTAs per SM while that stays under ~100 KB
+    const u32 p_max = ((size_t)EMIT_WARPS * t.G * 4 <= 100 * 1024 ? 2u : 1u) * ctx->sm_count;
+    const u32 n = std::max<u32>(ctx->n_handles, 1);
+    u32 chunk = (n + p_max - 1) / p_max;
+    chunk = std::max<u32>(CHUNK_ALIGN, (chunk + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN);
+    t.chunk = chunk;
+    t.P = (n + chunk - 1) / chunk;
+    return t;
+}
+
+int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw,
+                      const uint8_t* blocked, TickLayout* lay_out) {
+    const u32 R = ctx->R, Q = ctx->Q;
+    const TickLayout lay = tick_layout(W, R, Q, blocked != nullptr);
+    if (lay.bytes > ctx->tickin_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_tickin) CU(cudaFree(ctx->d_tickin));
+        if (ctx->h_tickin) CU(cudaFreeHost(ctx->h_tickin));
+        ctx->tickin_cap = lay.bytes * 2;
+        CU(cudaMalloc(&ctx->d_tickin, ctx->tickin_cap));
+        CU(cudaMallocHost(&ctx->h_tickin, ctx->tickin_cap));
+    }
+    unsigned char* h = ctx->h_tickin;
+    memcpy(h + lay.off_free, free_rw, (size_t)W * R * 8);
+    memcpy(h + lay.off_total, total_rw, (size_t)W * R * 8);
+    u64* rem = reinterpret_cast<u64*>(h + lay.off_rem);
+    for (u32 w = 0; w < W; ++w) rem[w] = workers[w].remaining_time_ms;
+    class_order(ctx, W, free_rw, total_rw, reinterpret_cast<u32*>(h + lay.off_order));
+    if (blocked) {
+        // ABI bit index ((w*Q + c) * HQS_MAX_VARIANTS + v) with HQS_MAX_VARIANTS == 8: one byte per (w, c)
+        memcpy(h + lay.off_blocked, blocked, (size_t)W * Q);
+    }
+    CU(cudaMemcpyAsync(ctx->d_tickin, h, lay.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *lay_out = lay;
+    return HQS_OK;
+}
+
+int validate_workers(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw) {
+    if (!workers || !free_rw || !total_rw) return fail(ctx, HQS_E_INVALID, "null worker arrays");
+    if (W == 0 || W > HQS_MAX_WORKERS) return fail(ctx, HQS_E_LIMIT, "n_workers=%u outside 1..%u", W, HQS_MAX_WORKERS);
+    for (u32 w = 1; w < W; ++w)
+        if (workers[w].worker_id <= workers[w - 1].worker_id)
+            return fail(ctx, HQS_E_INVALID, "workers must be sorted by ascending unique worker_id");
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
+    return HQS_OK;
+}
+
+int launch_count(hqs_ctx* ctx, const TickGeom& t) {
+    ctx->ev_valid = false;
+    if (ctx->profile) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    count_k<<<t.P, EMIT_THREADS, t.G * sizeof(u32), ctx->stream>>>(ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G,
+                                                                   ctx->d_table, ctx->d_total);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    if (ctx->profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    return HQS_OK;
+}
+
+int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, bool blocked,
+                      const u32* d_counts_all, const u32* d_before, u32 out_cap) {
+    SolveArgs a;
+    a.free_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_free);
+    a.total_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_total);
+    a.rem_time = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_rem);
+    a.order = reinterpret_cast<const u32*>(ctx->d_tickin + lay.off_order);
+    a.blocked = blocked ? ctx->d_tickin + lay.off_blocked : nullptr;
+    a.classes = ctx->d_classes;
+    a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
+    a.total_local = ctx->d_total;
+    a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
+    a.before = d_before;
+    a.gout = ctx->d_gout;
+    a.seg_cum = ctx->d_seg_cum; a.seg_wv = ctx->d_seg_wv;
+    a.free_after = ctx->d_free_after;
+    a.hdr = ctx->d_hdr;
+    a.glist = ctx->d_glist;
+    a.table = ctx->d_table; a.P = t.P;
+    const u32 threads = std::max<u32>(64, (W + 31) / 32 * 32);
+    const u32 scan_ctas = (t.G + threads - 1) / threads;
+    if (ctx->R <= 4) solve_k<4><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
+    else if (ctx->R <= 8) solve_k<8><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
+    else solve_k<16><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    emit_k<<<t.P, EMIT_THREADS, (size_t)EMIT_WARPS * t.G * sizeof(u32), ctx->stream>>>(
+        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
+        ctx->d_seg_wv, ctx->d_out, out_cap);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    if (ctx->profile) { CU(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid = true; }
+    ctx->last_W = W; ctx->last_G = t.G; ctx->last_L = t.L;
+    ctx->tick_pending = true;
+    ctx->stats.ticks++;
+    return HQS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int hqs_abi_version(void) { return HQS_ABI_VERSION; }
+
+const char* hqs_last_error(const hqs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) {
+    hqs_ctx* ctx = nullptr;
+    (void)flags;
+    if (!out) return fail(nullptr, HQS_E_INVALID, "out is null");
+    *out = nullptr;
+    if (n_resources == 0 || n_resources > HQS_MAX_RESOURCES)
+        return fail(nullptr, HQS_E_LIMIT, "n_resources=%u outside 1..%u", n_resources, HQS_MAX_RESOURCES);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, HQS_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(nullptr, HQS_E_INVALID, "device %d out of range", device);
+    ctx = new (std::nothrow) hqs_ctx();
+    if (!ctx) return fail(nullptr, HQS_E_NOMEM, "out of memory");
+    ctx->device = device;
+    ctx->R = n_resources;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newcnt, sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(EMIT_WARPS * HQS_MAX_GROUPS * sizeof(u32)));
+    if (e != cudaSuccess) {
+        fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return HQS_E_CUDA;
+    }
+    ctx->sm_count = sms > 0 ? (u32)sms : 148;
+    *out = ctx;
+    return HQS_OK;
+}
+
+void hqs_destroy(hqs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* dev_ptrs[] = {ctx->d_classes, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
+                        ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
+                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_glist, ctx->d_seg_cum,
+                        ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin};
+    for (void* p : dev_ptrs) if (p) cudaFree(p);
+    if (ctx->h_tickin) cudaFreeHost(ctx->h_tickin);
+    if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!classes || n_classes == 0) return fail(ctx, HQS_E_INVALID, "empty class table");
+    if (n_classes > HQS_MAX_CLASSES) return fail(ctx, HQS_E_LIMIT, "n_classes=%u > %u", n_classes, HQS_MAX_CLASSES);
+    std::vector<DevClass> dev(n_classes);
+    for (u32 c = 0; c < n_classes; ++c) {
+        const hqs_class& s = classes[c];
+        if (s.n_nodes != 0) return fail(ctx, HQS_E_INVALID, "class %u: multi-node requests are outside this path", c);
+        if (s.n_variants == 0 || s.n_variants > HQS_MAX_VARIANTS)
+            return fail(ctx, HQS_E_LIMIT, "class %u: n_variants=%u outside 1..%u", c, s.n_variants, HQS_MAX_VARIANTS);
+        DevClass& d = dev[c];
+        memset(&d, 0, sizeof d);
+        d.n_variants = s.n_variants;
+        for (u32 v = 0; v < s.n_variants; ++v) {
+            u32 used = 0;
+            for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) {
+                const bool all = (s.variants[v].all_mask >> r) & 1;
+                const u64 amt = s.variants[v].amount[r];
+                if ((all || amt) && r >= ctx->R)
+                    return fail(ctx, HQS_E_INVALID, "class %u variant %u uses resource %u >= n_resources", c, v, r);
+                d.v[v].amount[r] = all ? 0 : amt;
+                if (all || amt) used |= 1u << r;
+            }
+            if (!used) return fail(ctx, HQS_E_INVALID, "class %u variant %u: empty request (request.rs:191-194)", c, v);
+            if (s.variants[v].weight == 0) return fail(ctx, HQS_E_INVALID, "class %u variant %u: zero weight", c, v);
+            d.v[v].all_mask = s.variants[v].all_mask & ((1u << ctx->R) - 1);
+            d.v[v].used_mask = used;
+            d.v[v].min_time_ms = s.variants[v].min_time_ms;
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (n_classes > ctx->d_classes_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_classes) CU(cudaFree(ctx->d_classes));
+        ctx->d_classes_cap = std::max<u32>(n_classes * 2, 16);
+        CU(cudaMalloc(&ctx->d_classes, ctx->d_classes_cap * sizeof(DevClass)));
+    }
+    CU(cudaMemcpyAsync(ctx->d_classes, dev.data(), n_classes * sizeof(DevClass), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const bool q_changed = ctx->Q != n_classes;
+    ctx->classes.assign(classes, classes + n_classes);
+    ctx->Q = n_classes;
+    if (q_changed && !ctx->levels.empty()) {
+        // the level budget depends on Q: re-derive (possibly coarsened) levels and re-key the table
+        const bool was_coarse = ctx->coarse;
+        const size_t old_n = ctx->dev_levels.size();
+        int rc = upload_levels(ctx);
+        if (rc) return rc;
+        if (was_coarse || ctx->coarse || old_n != ctx->dev_levels.size())
+            if ((rc = relevel_all(ctx))) return rc;
+    }
+    return HQS_OK;
+}
+
+int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
+                   const uint64_t* priority) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n == 0) return HQS_OK;
+    if (!task || !class_id || !priority) return fail(ctx, HQS_E_INVALID, "null task arrays");
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
+    if (ctx->dag) return fail(ctx, HQS_E_STATE, "hqs_ready_push is not available after hqs_dag_load");
+    CU(cudaSetDevice(ctx->device));
+    u32 max_h = 0, max_c = 0;
+    for (u32 i = 0; i < n; ++i) { max_h = std::max(max_h, task[i]); max_c = std::max(max_c, class_id[i]); }
+    if (max_c >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", max_c, ctx->Q);
+    if (max_h == ~0u) return fail(ctx, HQS_E_INVALID, "task handle 0xFFFFFFFF is reserved");
+    int rc = ensure_handles(ctx, max_h + 1);
+    if (rc) return rc;
+    ctx->n_handles = std::max(ctx->n_handles, max_h + 1);
+    ctx->stats.n_handles = ctx->n_handles;
+    if (n > ctx->push_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_push_task) { CU(cudaFree(ctx->d_push_task)); CU(cudaFree(ctx->d_push_cls)); CU(cudaFree(ctx->d_push_prio)); }
+        ctx->push_cap = std::max<u32>(n, 1u << 16);
+        CU(cudaMalloc(&ctx->d_push_task, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_cls, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_prio, (size_t)ctx->push_cap * 8));
+    }
+    CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_push_cls, class_id, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_push_prio, priority, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_newcnt, 0, sizeof(u32), ctx->stream));
+    push_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_key,
+                                                     ctx->d_prio, ctx->d_levels, (u32)ctx->dev_levels.size(),
+                                                     ctx->coarse ? 1 : 0, ctx->d_newcnt, ctx->d_newprio);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_small, ctx->d_newcnt, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const u32 newcnt = ctx->h_small[0];
+    if (newcnt) {
+        std::vector<u64> fresh;
+        if (newcnt <= NEWPRIO_CAP) {
+            fresh.resize(newcnt);
+            CU(cudaMemcpy(fresh.data(), ctx->d_newprio, newcnt * sizeof(u64), cudaMemcpyDeviceToHost));
+        } else {
+            distinct_priorities(priority, n, fresh);
+        }
+        merge_levels(ctx, fresh);
+        if ((rc = upload_levels(ctx))) return rc;
+        if ((rc = relevel_all(ctx))) return rc;
+    }
+    return HQS_OK;
+}
+
+int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n == 0) return HQS_OK;
+    if (!task) return fail(ctx, HQS_E_INVALID, "null task array");
+    CU(cudaSetDevice(ctx->device));
+    if (n > ctx->push_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_push_task) { CU(cudaFree(ctx->d_push_task)); CU(cudaFree(ctx->d_push_cls)); CU(cudaFree(ctx->d_push_prio)); }
+        ctx->push_cap = std::max<u32>(n, 1u << 16);
+        CU(cudaMalloc(&ctx->d_push_task, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_cls, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_prio, (size_t)ctx->push_cap * 8));
+    }
+    CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    remove_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_task, ctx->d_key, ctx->n_handles);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HQS_OK;
+}
+
+int hqs_ready_rearm(hqs_ctx* ctx) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!ctx->n_handles) return HQS_OK;
+    CU(cudaSetDevice(ctx->device));
+    rearm_k<<<(ctx->n_handles + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_handles, ctx->d_key);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    return HQS_OK;
+}
+
+int hqs_dag_load(hqs_ctx* ctx, uint32_t n_tasks, const uint32_t* class_id, const uint64_t* priority,
+                 const uint32_t* n_deps, const uint32_t* cons_off, const uint32_t* cons) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!n_tasks || !class_id || !priority || !n_deps || !cons_off) return fail(ctx, HQS_E_INVALID, "null DAG arrays");
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
+    const u32 n_edges = cons_off[n_tasks];
+    if (n_edges && !cons) return fail(ctx, HQS_E_INVALID, "null consumer array");
+    for (u32 i = 0; i < n_tasks; ++i)
+        if (class_id[i] >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", class_id[i], ctx->Q);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_handles(ctx, n_tasks);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_deps) { CU(cudaFree(ctx->d_deps)); ctx->d_deps = nullptr; }
+    if (ctx->d_cons_off) { CU(cudaFree(ctx->d_cons_off)); ctx->d_cons_off = nullptr; }
+    if (ctx->d_cons) { CU(cudaFree(ctx->d_cons)); ctx->d_cons = nullptr; }
+    u32* d_cls = nullptr;
+    CU(cudaMalloc(&ctx->d_deps, (size_t)n_tasks * 4));
+    CU(cudaMalloc(&ctx->d_cons_off, ((size_t)n_tasks + 1) * 4));
+    CU(cudaMalloc(&ctx->d_cons, std::max<size_t>(n_edges, 1) * 4));
+    CU(cudaMalloc(&d_cls, (size_t)n_tasks * 4));
+    CU(cudaMemsetAsync(ctx->d_key, 0, (size_t)ctx->cap_handles * 4, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_deps, n_deps, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cons_off, cons_off, ((size_t)n_tasks + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_edges) CU(cudaMemcpyAsync(ctx->d_cons, cons, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_cls, class_id, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_prio, priority, (size_t)n_tasks * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<u64> fresh;
+    distinct_priorities(priority, n_tasks, fresh);
+    ctx->levels.clear();
+    merge_levels(ctx, fresh);
+    if ((rc = upload_levels(ctx))) { cudaFree(d_cls); return rc; }
+    ctx->n_handles = n_tasks;
+    ctx->stats.n_handles = n_tasks;
+    dag_init_k<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>(n_tasks, d_cls, ctx->d_prio, ctx->d_deps, ctx->d_key,
+                                                               ctx->d_levels, (u32)ctx->dev_levels.size(),
+                                                               ctx->coarse ? 1 : 0);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(d_cls));
+    ctx->dag = true;
+    return HQS_OK;
+}
+
+int hqs_tasks_finished(hqs_ctx* ctx, uint32_t n, const uint32_t* task, uint32_t* n_new_ready) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n_new_ready) *n_new_ready = 0;
+    if (!ctx->dag) return fail(ctx, HQS_E_STATE, "hqs_tasks_finished needs hqs_dag_load");
+    if (n == 0) return HQS_OK;
+    if (!task) return fail(ctx, HQS_E_INVALID, "null task array");
+    CU(cudaSetDevice(ctx->device));
+    if (n > ctx->push_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_push_task) { CU(cudaFree(ctx->d_push_task)); CU(cudaFree(ctx->d_push_cls)); CU(cudaFree(ctx->d_push_prio)); }
+        ctx->push_cap = std::max<u32>(n, 1u << 16);
+        CU(cudaMalloc(&ctx->d_push_task, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_cls, (size_t)ctx->push_cap * 4));
+        CU(cudaMalloc(&ctx->d_push_prio, (size_t)ctx->push_cap * 8));
+    }
+    CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_newcnt, 0, sizeof(u32), ctx->stream));
+    finished_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_task, ctx->d_cons_off, ctx->d_cons, ctx->d_deps,
+                                                         ctx->d_key, ctx->d_newcnt);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    if (n_new_ready) {
+        CU(cudaMemcpyAsync(ctx->h_small, ctx->d_newcnt, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *n_new_ready = ctx->h_small[0];
+    }
+    return HQS_OK;
+}
+
+int hqs_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+                    const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap) {
+    if (!ctx) return HQS_E_INVALID;
+    int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
+    if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap))) return rc;
+    TickLayout lay;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
+    if (ctx->n_handles == 0) {
+        // nothing was ever pushed: an empty tick still has to produce a header
+        CU(cudaMemsetAsync(ctx->d_hdr, 0, sizeof(TickHeaderOut), ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_free_after, ctx->d_tickin + lay.off_free, (size_t)n_workers * ctx->R * 8,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->last_W = n_workers; ctx->tick_pending = true; ctx->stats.ticks++;
+        return HQS_OK;
+    }
+    if ((rc = launch_count(ctx, t))) return rc;
+    return launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, out_cap);
+}
+
+int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t* out_n, uint64_t* free_after) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!ctx->tick_pending) return fail(ctx, HQS_E_STATE, "no tick in flight");
+    if (out_n) *out_n = 0;
+    CU(cudaSetDevice(ctx->device));
+    const size_t fa_bytes = (size_t)ctx->last_W * ctx->R * 8;
+    const size_t need = sizeof(TickHeaderOut) + fa_bytes;
+    if (need > ctx->h_hdr_cap) {
+        if (ctx->h_hdr) CU(cudaFreeHost(ctx->h_hdr));
+        ctx->h_hdr_cap = need * 2;
+        CU(cudaMallocHost(&ctx->h_hdr, ctx->h_hdr_cap));
+    }
+    CU(cudaMemcpyAsync(ctx->h_hdr, ctx->d_hdr, sizeof(TickHeaderOut), cudaMemcpyDeviceToHost, ctx->stream));
+    if (free_after)
+        CU(cudaMemcpyAsync(ctx->h_hdr + sizeof(TickHeaderOut), ctx->d_free_after, fa_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->tick_pending = false;
+    TickHeaderOut hdr;
+    memcpy(&hdr, ctx->h_hdr, sizeof hdr);
+    ctx->stats.n_groups = hdr.n_groups;
+    ctx->stats.n_levels = ctx->last_L;
+    ctx->stats.n_assigned = hdr.n_assigned;
+    ctx->stats.n_segments = hdr.n_segments;
+    if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
+    if (hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
+        return fail(ctx, HQS_E_OVERFLOW, "out_cap=%u too small for %u assignments", out_cap, hdr.n_assigned);
+    if (free_after) memcpy(free_after, ctx->h_hdr + sizeof(TickHeaderOut), fa_bytes);
+    if (hdr.n_assigned) {
+        CU(cudaMemcpyAsync(out, ctx->d_out, (size_t)hdr.n_assigned * sizeof(hqs_assignment), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (out_n) *out_n = hdr.n_assigned;
+    return HQS_OK;
+}
+
+int hqs_tick(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+             const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap, hqs_assignment* out,
+             uint32_t* out_n, uint64_t* free_after) {
+    int rc = hqs_tick_launch(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, out_cap);
+    if (rc) return rc;
+    return hqs_tick_fetch(ctx, out_cap, out, out_n, free_after);
+}
+
+int hqs_shard_count(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+                    const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t* d_counts, uint32_t n_groups_cap,
+                    uint32_t* n_groups) {
+    if (!ctx) return HQS_E_INVALID;
+    int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
+    if (rc) return rc;
+    if (!d_counts) return fail(ctx, HQS_E_INVALID, "null d_counts");
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
+    if (t.G > n_groups_cap) return fail(ctx, HQS_E_LIMIT, "groups=%u > n_groups_cap=%u", t.G, n_groups_cap);
+    if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, 1024))) return rc;
+    TickLayout lay;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
+    if (ctx->n_handles) {
+        if ((rc = launch_count(ctx, t))) return rc;
+    }
+    CU(cudaMemsetAsync(d_counts, 0, (size_t)n_groups_cap * 4, ctx->stream));
+    CU(cudaMemcpyAsync(d_counts, ctx->d_total, (size_t)t.G * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->last_W = n_workers;
+    ctx->h_small[8] = blocked_wcv ? 1u : 0u;
+    if (n_groups) *n_groups = t.G;
+    return HQS_OK;
+}
+
+int hqs_shard_solve_emit(hqs_ctx* ctx, const uint32_t* d_counts_all, const uint32_t* d_ranks_before, uint32_t out_cap) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!d_counts_all || !d_ranks_before) return fail(ctx, HQS_E_INVALID, "null count vectors");
+    if (!ctx->last_W) return fail(ctx, HQS_E_STATE, "hqs_shard_count has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    int rc = ensure_tick_buffers(ctx, t.G, t.P, ctx->last_W, out_cap);
+    if (rc) return rc;
+    const TickLayout lay = tick_layout(ctx->last_W, ctx->R, ctx->Q, ctx->h_small[8] != 0);
+    return launch_solve_emit(ctx, t, ctx->last_W, lay, ctx->h_small[8] != 0, d_counts_all, d_ranks_before, out_cap);
+}
+
+int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n) {
+    if (!ctx) return HQS_E_INVALID;
+    if (d_out) *d_out = ctx->d_out;
+    if (d_out_n) *d_out_n = ctx->d_hdr ? &ctx->d_hdr->n_assigned : nullptr;
+    return HQS_OK;
+}
+
+void* hqs_stream(hqs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int hqs_set_stream(hqs_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return HQS_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) CU(cudaStreamDestroy(ctx->stream));
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return HQS_OK;
+}
+
+int hqs_set_profile(hqs_ctx* ctx, int on) {
+    if (!ctx) return HQS_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ctx->ev[i]));
+    ctx->profile = on != 0;
+    ctx->ev_valid = false;
+    return HQS_OK;
+}
+
+int hqs_get_kernel_ms(hqs_ctx* ctx, float out_ms[4]) {
+    if (!ctx || !out_ms) return HQS_E_INVALID;
+    if (!ctx->profile || !ctx->ev_valid) return fail(ctx, HQS_E_STATE, "no profiled tick available");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev[3]));
+    out_ms[3] = 0;
+    for (int i = 0; i < 3; ++i) {
+        CU(cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+        out_ms[3] += out_ms[i];
+    }
+    return HQS_OK;
+}
+
+int hqs_sync(hqs_ctx* ctx) {
+    if (!ctx) return HQS_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HQS_OK;
+}
+
+int hqs_get_stats(hqs_ctx* ctx, hqs_stats* out) {
+    if (!ctx || !out) return HQS_E_INVALID;
+    *out = ctx->stats;
+    out->n_levels = (u32)ctx->dev_levels.size();
+    return HQS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""Host-side mirror of tako's scheduler seam over the C ABI (include/hqsched.h).
+
+What the Rust shim of INTEGRATION.md does inside `run_scheduling_inner`
+(/root/reference/crates/tako/src/internal/scheduler/main.rs:40-46) is done here in Python so that the
+parity tests and the benchmark read like the reference's own tests:
+
+  reference (Rust)                                          here
+  --------------------------------------------------------  -----------------------------------------
+  get_or_create_resource_rq_id   control.rs:222-227         GpuScheduler.get_or_create_resource_rq_id
+  on_new_worker                  reactor.rs:20-32           GpuScheduler.new_worker
+  Worker::block_request          worker.rs:336-344          GpuScheduler.block_request / unblock_request
+  TaskQueues::add_ready_task     taskqueue.rs:37-43         GpuScheduler.add_ready_tasks
+  TaskQueue::remove              taskqueue.rs:194-216       GpuScheduler.remove_ready_tasks
+  run_scheduling_inner           main.rs:40-46              GpuScheduler.run_scheduling  -> WorkerTaskMapping
+  Worker::insert_sn_task         worker.rs:188-196          (free vectors come back from the device)
+  task_finished / remove_sn_task reactor.rs:500-580         GpuScheduler.tasks_finished
+
+Device memory, streams and the kernels live in libhqsched_b200.so; this module only marshals numpy
+arrays.  No CPU fallback exists: without the library or a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+FRACTIONS_PER_UNIT = 10_000
+
+
+def priority_from_user(user_priority) -> np.ndarray:
+    """Priority::from_user_priority (common/priority.rs:43-48), vectorised."""
+    p = np.asarray(user_priority, dtype=np.int64)
+    return ((((p & 0xFFFFFFFF) ^ 0x8000_0000).astype(np.uint64)) << np.uint64(32)).astype(np.uint64)
+
+
+@dataclass(frozen=True)
+class RequestVariant:
+    """One ResourceRequest (common/resources/request.rs:136-167) in dense form."""
+    amounts: Tuple[Tuple[int, int], ...]          # (resource id, fractions), amount policies
+    all_resources: Tuple[int, ...] = ()           # resource ids requested with policy `All`
+    weight: float = 1.0
+    min_time_s: float = 0.0
+
+    @staticmethod
+    def of(amounts: Dict[int, int], all_resources: Iterable[int] = (), weight: float = 1.0,
+           min_time_s: float = 0.0) -> "RequestVariant":
+        return RequestVariant(tuple(sorted((int(r), int(a)) for r, a in amounts.items())),
+                              tuple(sorted(int(r) for r in all_resources)), float(weight), float(min_time_s))
+
+
+@dataclass
+class WorkerTaskMapping:
+    """What create_task_mapping returns (mapping.rs:9-21), as arrays."""
+    assignments: np.ndarray                       # L.assignment_dtype; `worker` = index into worker_ids
+    worker_ids: np.ndarray
+    free_after: np.ndarray                        # [W][R] u64
+
+    def n_assigned(self) -> int:
+        return int(self.assignments.shape[0])
+
+    def per_worker(self) -> Dict[int, List[Tuple[int, int]]]:
+        """worker_id -> [(task handle, variant)] in emission order (priority descending)."""
+        out: Dict[int, List[Tuple[int, int]]] = {}
+        a = self.assignments
+        for t, w, v in zip(a["task"].tolist(), a["worker"].tolist(), a["variant"].tolist()):
+            out.setdefault(int(self.worker_ids[w]), []).append((t, v))
+        return out
+
+
+class GpuScheduler:
+    def __init__(self, n_resources: int, device: int = 0) -> None:
+        self._lib = L.load_library()
+        self.R = int(n_resources)
+        self._ctx = C.c_void_p()
+        rc = self._lib.hqs_create(C.byref(self._ctx), device, self.R, 0)
+        if rc:
+            raise L.HqsError(rc, (self._lib.hqs_last_error(None) or b"").decode())
+        self._rq_ids: Dict[Tuple[RequestVariant, ...], int] = {}
+        self._classes: List[Tuple[RequestVariant, ...]] = []
+        self._classes_dirty = False
+        # dense per-class amount table for resource return: [Q][V][R] and an `All` mask [Q][V][R]
+        self._amount_tab = np.zeros((0, L.HQS_MAX_VARIANTS, self.R), dtype=np.uint64)
+        self._all_tab = np.zeros((0, L.HQS_MAX_VARIANTS, self.R), dtype=bool)
+        # workers, kept sorted by id
+        self.worker_ids = np.zeros(0, dtype=np.uint32)
+        self.total = np.zeros((0, self.R), dtype=np.uint64)
+        self.free = np.zeros((0, self.R), dtype=np.uint64)
+        self.termination = np.zeros(0, dtype=np.float64)      # absolute seconds, inf = none
+        self.min_utilization = np.zeros(0, dtype=np.float32)
+        self._blocked: Dict[int, set] = {}
+        # per-task host mirror (Task.resource_rq_id / TaskRuntimeState::Assigned{worker_id, rv_id})
+        self._task_class = np.zeros(0, dtype=np.uint32)
+        self._task_worker = np.zeros(0, dtype=np.int64)
+        self._task_variant = np.zeros(0, dtype=np.uint8)
+        self._out = np.zeros(1024, dtype=L.assignment_dtype)
+
+    # ------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.hqs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise L.HqsError(rc, (self._lib.hqs_last_error(self._ctx) or b"").decode())
+
+    # classes ----------------------------------------------------------------------------------
+    def get_or_create_resource_rq_id(self, variants: Sequence[RequestVariant]) -> int:
+        key = tuple(variants)
+        rid = self._rq_ids.get(key)
+        if rid is None:
+            if not 1 <= len(key) <= L.HQS_MAX_VARIANTS:
+                raise ValueError("1..%d variants per class" % L.HQS_MAX_VARIANTS)
+            rid = len(self._classes)
+            self._rq_ids[key] = rid
+            self._classes.append(key)
+            self._classes_dirty = True
+        return rid
+
+    @property
+    def n_classes(self) -> int:
+        return len(self._classes)
+
+    def _sync_classes(self) -> None:
+        if not self._classes_dirty:
+            return
+        q = len(self._classes)
+        arr = (L.hqs_class * q)()
+        self._amount_tab = np.zeros((q, L.HQS_MAX_VARIANTS, self.R), dtype=np.uint64)
+        self._all_tab = np.zeros((q, L.HQS_MAX_VARIANTS, self.R), dtype=bool)
+        for c, variants in enumerate(self._classes):
+            arr[c].n_variants = len(variants)
+            arr[c].n_nodes = 0
+            for v, rv in enumerate(variants):
+                hv = arr[c].variants[v]
+                for r, a in rv.amounts:
+                    if a <= 0:
+                        raise ValueError("Zero resources cannot be requested")   # request.rs:24-32
+                    hv.amount[r] = a
+                    self._amount_tab[c, v, r] = a
+                mask = 0
+                for r in rv.all_resources:
+                    mask |= 1 << r
+                    self._all_tab[c, v, r] = True
+                hv.all_mask = mask
+                hv.weight = int(np.round(np.float32(rv.weight) * np.float32(10_000)))
+                hv.min_time_ms = int(round(rv.min_time_s * 1000.0))
+        self._check(self._lib.hqs_classes_set(self._ctx, q, arr))
+        self._classes_dirty = False
+
+    # workers ----------------------------------------------------------------------------------
+    def new_worker(self, worker_id: int, resources: Sequence[int], termination_time: Optional[float] = None,
+                   min_utilization: float = 0.0, free: Optional[Sequence[int]] = None) -> None:
+        if worker_id in self.worker_ids:
+            raise ValueError(f"worker {worker_id} exists")
+        tot = np.zeros(self.R, dtype=np.uint64)
+        tot[: len(resources)] = np.asarray(resources, dtype=np.uint64)
+        fr = tot.copy() if free is None else np.asarray(list(free) + [0] * (self.R - len(free)), dtype=np.uint64)
+        pos = int(np.searchsorted(self.worker_ids, worker_id))
+        self.worker_ids = np.insert(self.worker_ids, pos, worker_id).astype(np.uint32)
+        self.total = np.insert(self.total, pos, tot, axis=0)
+        self.free = np.insert(self.free, pos, fr, axis=0)
+        self.termination = np.insert(self.termination, pos, np.inf if termination_time is None else termination_time)
+        self.min_utilization = np.insert(self.min_utilization, pos, min_utilization).astype(np.float32)
+
+    def new_workers_bulk(self, worker_ids: np.ndarray, total: np.ndarray, free: Optional[np.ndarray] = None) -> None:
+        order = np.argsort(worker_ids)
+        self.worker_ids = np.asarray(worker_ids, dtype=np.uint32)[order]
+        self.total = np.ascontiguousarray(np.asarray(total, dtype=np.uint64)[order])
+        self.free = self.total.copy() if free is None else np.ascontiguousarray(np.asarray(free, dtype=np.uint64)[order])
+        self.termination = np.full(len(order), np.inf)
+        self.min_utilization = np.zeros(len(order), dtype=np.float32)
+
+    def block_request(self, worker_id: int, rq_id: int, variant: int) -> None:
+        self._blocked.setdefault(worker_id, set()).add((rq_id, variant))
+
+    def unblock_request(self, worker_id: int, rq_id: int, variant: int) -> None:
+        self._blocked.get(worker_id, set()).discard((rq_id, variant))
+
+    def set_blocked_mask(self, mask_wcv: Optional[np.ndarray]) -> None:
+        """Bulk form: bool [W][Q][HQS_MAX_VARIANTS] over the sorted workers, or None."""
+        self._blocked_bulk = None if mask_wcv is None else np.packbits(
+            np.asarray(mask_wcv, dtype=bool), axis=2, bitorder="little")[:, :, 0].copy()
+
+    # ready set ----------------------------------------------------------------------------------
+    def _grow_tasks(self, n: int) -> None:
+        if n > self._task_class.shape[0]:
+            m = max(n, 2 * self._task_class.shape[0], 1024)
+            self._task_class = np.concatenate([self._task_class, np.zeros(m - self._task_class.shape[0], np.uint32)])
+            self._task_worker = np.concatenate([self._task_worker, np.full(m - self._task_worker.shape[0], -1, np.int64)])
+            self._task_variant = np.concatenate([self._task_variant, np.zeros(m - self._task_variant.shape[0], np.uint8)])
+
+    def add_ready_tasks(self, handles, rq_ids, priorities) -> None:
+        h = np.ascontiguousarray(handles, dtype=np.uint32)
+        c = np.ascontiguousarray(rq_ids, dtype=np.uint32)
+        p = np.ascontiguousarray(priorities, dtype=np.uint64)
+        if not (h.shape == c.shape == p.shape):
+            raise ValueError("shape mismatch")
+        if h.size == 0:
+            return
+        self._sync_classes()
+        self._grow_tasks(int(h.max()) + 1)
+        self._task_class[h] = c
+        self._check(self._lib.hqs_ready_push(self._ctx, h.size, L.ptr(h), L.ptr(c), L.ptr(p)))
+
+    def remove_ready_tasks(self, handles) -> None:
+        h = np.ascontiguousarray(handles, dtype=np.uint32)
+        if h.size:
+            self._check(self._lib.hqs_ready_remove(self._ctx, h.size, L.ptr(h)))
+
+    def load_dag(self, rq_ids, priorities, n_deps, cons_off, cons) -> None:
+        c = np.ascontiguousarray(rq_ids, dtype=np.uint32)
+        p = np.ascontiguousarray(priorities, dtype=np.uint64)
+        d = np.ascontiguousarray(n_deps, dtype=np.uint32)
+        co = np.ascontiguousarray(cons_off, dtype=np.uint32)
+        cs = np.ascontiguousarray(cons, dtype=np.uint32)
+        self._sync_classes()
+        self._grow_tasks(c.size)
+        self._task_class[: c.size] = c
+        self._check(self._lib.hqs_dag_load(self._ctx, c.size, L.ptr(c), L.ptr(p), L.ptr(d), L.ptr(co),
+                                           L.ptr(cs) if cs.size else None))
+
+    # the tick -----------------------------------------------------------------------------------
+    def _worker_structs(self, now: float) -> np.ndarray:
+        w = np.zeros(self.worker_ids.shape[0], dtype=L.worker_dtype)
+        w["worker_id"] = self.worker_ids
+        rem = np.where(np.isinf(self.termination), np.float64(L.HQS_TIME_INF),
+                       np.maximum(self.termination - now, 0.0) * 1000.0)
+        w["remaining_time_ms"] = np.where(np.isinf(self.termination), np.uint64(L.HQS_TIME_INF),
+                                          rem.astype(np.uint64))
+        w["min_utilization"] = self.min_utilization
+        return w
+
+    def _blocked_bytes(self) -> Optional[np.ndarray]:
+        bulk = getattr(self, "_blocked_bulk", None)
+        if bulk is not None:
+            return np.ascontiguousarray(bulk, dtype=np.uint8)
+        if not any(self._blocked.values()):
+            return None
+        q = len(self._classes)
+        b = np.zeros((self.worker_ids.shape[0], q), dtype=np.uint8)
+        for wid, pairs in self._blocked.items():
+            pos = int(np.searchsorted(self.worker_ids, wid))
+            if pos < self.worker_ids.shape[0] and self.worker_ids[pos] == wid:
+                for rq, v in pairs:
+                    if rq < q:
+                        b[pos, rq] |= np.uint8(1 << v)
+        return b
+
+    def run_scheduling(self, now: float = 0.0, out_cap: Optional[int] = None) -> WorkerTaskMapping:
+        """run_scheduling_inner: one tick over the device-resident ready set.  Assigned tasks leave the
+        ready set and the host free vectors are replaced by the post-tick vectors."""
+        self._sync_classes()
+        w = self._worker_structs(now)
+        nw = w.shape[0]
+        if out_cap is None:
+            out_cap = max(int(self._lib_stats().n_handles), 1)
+        if self._out.shape[0] < out_cap:
+            self._out = np.zeros(out_cap, dtype=L.assignment_dtype)
+        blocked = self._blocked_bytes()
+        free = np.ascontiguousarray(self.free)
+        total = np.ascontiguousarray(self.total)
+        free_after = np.zeros_like(free)
+        n = C.c_uint32(0)
+        self._check(self._lib.hqs_tick(self._ctx, nw, L.ptr(w), L.ptr(free), L.ptr(total),
+                                       L.ptr(blocked) if blocked is not None else None, out_cap,
+                                       L.ptr(self._out), C.byref(n), L.ptr(free_after)))
+        a = self._out[: n.value].copy()
+        self.free = free_after
+        if a.size:
+            self._task_worker[a["task"]] = a["worker"]
+            self._task_variant[a["task"]] = a["variant"]
+        return WorkerTaskMapping(a, self.worker_ids.copy(), free_after)
+
+    def tasks_finished(self, handles, propagate: bool = False) -> int:
+        """task_finished for a batch: returns the resources of each task to its worker
+        (Worker::remove_sn_task -> WorkerResources::add, workerload.rs:194-202).  With `propagate`
+        (DAG mode) the device also decrements the consumers' dependency counters and marks the
+        newly ready ones; returns how many became ready."""
+        h = np.ascontiguousarray(handles, dtype=np.uint32)
+        if h.size == 0:
+            return 0
+        wi = self._task_worker[h]
+        cl = self._task_class[h]
+        va = self._task_variant[h]
+        amounts = self._amount_tab[cl, va]                       # [n][R]
+        add = np.zeros_like(self.free)
+        np.add.at(add, wi, amounts)
+        self.free = self.free + add
+        allm = self._all_tab[cl, va]                             # [n][R] bool
+        if allm.any():
+            ws, rs = np.nonzero(allm)
+            self.free[wi[ws], rs] = self.total[wi[ws], rs]
+        self._task_worker[h] = -1
+        if propagate:
+            n_new = C.c_uint32(0)
+            self._check(self._lib.hqs_tasks_finished(self._ctx, h.size, L.ptr(h), C.byref(n_new)))
+            return int(n_new.value)
+        return 0
+
+    # misc ---------------------------------------------------------------------------------------
+    def rearm(self) -> None:
+        self._check(self._lib.hqs_ready_rearm(self._ctx))
+
+    def sync(self) -> None:
+        self._check(self._lib.hqs_sync(self._ctx))
+
+    def _lib_stats(self) -> L.hqs_stats:
+        st = L.hqs_stats()
+        self._check(self._lib.hqs_get_stats(self._ctx, C.byref(st)))
+        return st
+
+    def stats(self) -> Dict[str, int]:
+        st = self._lib_stats()
+        return {name: int(getattr(st, name)) for name, _ in L.hqs_stats._fields_}
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.hqs_stream(self._ctx) or 0)

@@ -1,0 +1,187 @@
+/*
+ * hqsched.h — C ABI of the B200-native task->worker assignment solver (libhqsched_b200.so).
+ *
+ * Drop-in boundary for the hot path of HyperQueue's tako scheduler tick (v0.26.0).  The reference has
+ * no FFI for this path; the seam it replaces is the pair
+ *     run_scheduling_solver()   crates/tako/src/internal/scheduler/solver.rs:16-461
+ *     create_task_mapping()     crates/tako/src/internal/scheduler/mapping.rs:23-154  (task selection half)
+ * called from run_scheduling_inner()  crates/tako/src/internal/scheduler/main.rs:40-46.
+ * A Rust shim keeps Core mutation and Comm::send_worker_message in Rust and calls
+ * this library through bindgen, the same way `highs-sys` binds HiGHS today (Cargo.lock:1116-1123).
+ *
+ * Conventions
+ *  - plain C, no exceptions / longjmp across the ABI, caller-owned host buffers (pinned or pageable),
+ *  - every function returns 0 on success and a negative HQS_E_* code on failure; after a failed
+ *    hqs_tick the host must schedule NOTHING this tick (mirrors "solver returned None => empty
+ *    solution", solver.rs:412-415); hqs_last_error() gives the text,
+ *  - called from tako's single reactor thread; a context is not thread-safe,
+ *  - tasks are named by dense u32 handles chosen by the shim IN TaskId ORDER (ascending handle ==
+ *    ascending (job_id, job_task_id)), because the ready set is popped in ascending TaskId inside one
+ *    priority level (scheduler/taskqueue.rs:395-420) and the device ranks tasks by handle,
+ *  - amounts are ResourceAmount fractions (u64, 10 000 per unit, common/resources/amount.rs:7,26);
+ *    ~0 is ResourceAmount::MAX ("unknown/unbounded", amount.rs:30),
+ *  - priorities are tako Priority values (u64, larger = more urgent, common/priority.rs:36-48).
+ */
+#ifndef HQSCHED_H
+#define HQSCHED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQS_ABI_VERSION 1
+#define HQS_MAX_RESOURCES 16u   /* resource kinds per context (R)                                  */
+#define HQS_MAX_VARIANTS 8u     /* variants per request class (reference allows 32, request.rs:305) */
+#define HQS_MAX_WORKERS 1024u   /* workers per tick (one solver thread per worker)                  */
+#define HQS_MAX_CLASSES 4096u   /* interned request classes (ResourceRqId)                          */
+#define HQS_MAX_GROUPS 4096u    /* (priority level x class) groups; levels are coarsened to fit     */
+#define HQS_AMOUNT_MAX (~(uint64_t)0)
+#define HQS_TIME_INF (~(uint64_t)0)
+
+enum {
+    HQS_OK = 0,
+    HQS_E_INVALID = -1,   /* bad argument                                   */
+    HQS_E_CUDA = -2,      /* CUDA runtime error (text in hqs_last_error)    */
+    HQS_E_LIMIT = -3,     /* a compile-time limit above was exceeded        */
+    HQS_E_NOMEM = -4,
+    HQS_E_OVERFLOW = -5,  /* out_cap too small for the assignments produced */
+    HQS_E_STATE = -6      /* call sequence error                            */
+};
+
+typedef struct hqs_ctx hqs_ctx;
+
+/* One variant of a request class = ResourceRequest (common/resources/request.rs:136-167) in dense
+ * per-resource form.  amount[r] == 0: resource r not requested.  Bit r of all_mask: policy `All`
+ * (request.rs:20): needs >= 1 fraction free to be feasible and consumes the worker's TOTAL of r
+ * (solver.rs:120-124).  The five amount policies (compact/tight/scatter/forced) are identical on the
+ * server side (request.rs:38-48) and are not distinguished here. */
+typedef struct {
+    uint64_t amount[HQS_MAX_RESOURCES];
+    uint32_t all_mask;
+    uint32_t weight;        /* ResourceWeight raw value, 10 000 = 1.0 (request.rs:107-134) */
+    uint64_t min_time_ms;   /* TimeRequest (request.rs:143-149) in milliseconds            */
+} hqs_variant;
+
+/* ResourceRequestVariants (request.rs:229-316), interned as ResourceRqId = index in the array given
+ * to hqs_classes_set (common/resources/map.rs:99-109).  n_nodes > 0 (multi-node) is rejected:
+ * multi-node placement is outside this path. */
+typedef struct {
+    uint32_t n_variants;
+    uint32_t n_nodes;
+    hqs_variant variants[HQS_MAX_VARIANTS];
+} hqs_class;
+
+/* Server-side view of one worker for one tick (server/worker.rs:63-84).  The array passed to
+ * hqs_tick must be sorted by ascending worker_id (solver.rs:44). */
+typedef struct {
+    uint32_t worker_id;
+    uint32_t flags;              /* reserved, 0                                                   */
+    uint64_t remaining_time_ms;  /* termination_time - now, HQS_TIME_INF if none (worker.rs:320)   */
+    float min_utilization;       /* WorkerConfiguration::min_utilization (solver.rs:154-156)       */
+    uint32_t reserved;
+} hqs_worker;
+
+/* One emitted placement.  8 bytes: the unit of the output stream. */
+typedef struct {
+    uint32_t task;     /* handle                                                         */
+    uint16_t worker;   /* INDEX into the workers[] array of this tick (not worker_id)    */
+    uint8_t variant;   /* ResourceVariantId                                              */
+    uint8_t kind;      /* 0 = assign (ComputeTasks with variant), 1 = prefill (reserved) */
+} hqs_assignment;
+
+typedef struct {
+    uint32_t n_groups;          /* non-empty (priority level, class) groups seen by the last tick */
+    uint32_t n_levels;          /* priority levels (after coarsening)                             */
+    uint32_t n_assigned;        /* assignments produced by the last tick                          */
+    uint32_t n_segments;        /* (group, worker, variant) count segments of the last tick       */
+    uint64_t kernel_launches;   /* kernels launched by this context so far                        */
+    uint64_t ticks;
+    uint32_t n_handles;         /* size of the device task table                                  */
+    uint32_t coarsened;         /* 1 if priority levels had to be merged to fit HQS_MAX_GROUPS    */
+} hqs_stats;
+
+int hqs_abi_version(void);
+
+/* Creates a context on CUDA device `device`.  n_resources = number of resource kinds (R <= 16). */
+int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags);
+void hqs_destroy(hqs_ctx* ctx);
+const char* hqs_last_error(const hqs_ctx* ctx);   /* ctx may be NULL: last error of hqs_create */
+
+/* Replaces the class table (mirror of ResourceRqMap; ids are array indices, append-only in tako). */
+int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes);
+
+/* TaskQueues::add_ready_task (taskqueue.rs:37-43) for n tasks: the task becomes ready with the given
+ * class and priority.  Handles may be new or re-used after the task left the ready set. */
+int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
+                   const uint64_t* priority);
+/* TaskQueue::remove (taskqueue.rs:194-216): cancel / externally assigned tasks leave the ready set. */
+int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task);
+
+/* DAG mode (reactor.rs:188-220 on_new_tasks + :500-580 task_finished, device resident): loads a whole
+ * task graph; tasks with n_deps == 0 are ready at once.  consumers of task t are
+ * cons[cons_off[t] .. cons_off[t+1]).  Handles are 0..n_tasks-1 and replace the current table. */
+int hqs_dag_load(hqs_ctx* ctx, uint32_t n_tasks, const uint32_t* class_id, const uint64_t* priority,
+                 const uint32_t* n_deps, const uint32_t* cons_off, const uint32_t* cons);
+/* task_finished for n tasks: decrements unfinished_deps of every consumer; consumers reaching zero
+ * become ready (add_ready_task).  *n_new_ready (optional) receives how many did. */
+int hqs_tasks_finished(hqs_ctx* ctx, uint32_t n, const uint32_t* task, uint32_t* n_new_ready);
+
+/* One scheduler tick over the current ready set (replaces run_scheduling_solver + the task-selection
+ * half of create_task_mapping).
+ *   workers[n_workers]            ascending worker_id
+ *   free_rw[n_workers][R]         SingleNodeTaskAssignment::free_resources   (worker.rs:44)
+ *   total_rw[n_workers][R]        Worker::resources                          (worker.rs:69)
+ *   blocked_wcv                   optional bitmask, bit index ((w * n_classes + c) * HQS_MAX_VARIANTS + v),
+ *                                 LSB-first in bytes: Worker::blocked_requests (worker.rs:70,328-344)
+ *   out[out_cap], *out_n          assignments, ordered by (priority desc, class order of this tick,
+ *                                 handle asc) — per worker that is already the priority-descending
+ *                                 order mapping.rs:125-128 sorts into
+ *   free_after[n_workers][R]      optional: free vectors after the tick's assignments
+ * Assigned tasks leave the ready set (Waiting -> Assigned, mapping.rs:55-66). */
+int hqs_tick(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+             const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap,
+             hqs_assignment* out, uint32_t* out_n, uint64_t* free_after);
+
+/* Split form of hqs_tick for pipelining / device-side timing: launch enqueues the upload of the worker
+ * state and the tick kernels on the context stream and returns; fetch waits and copies the result.
+ * hqs_tick(...) == hqs_tick_launch(...) followed by hqs_tick_fetch(...). */
+int hqs_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
+                    const uint64_t* free_rw, const uint64_t* total_rw, const uint8_t* blocked_wcv,
+                    uint32_t out_cap);
+int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t* out_n,
+                   uint64_t* free_after);
+
+/* Multi-GPU sharding: each rank owns a contiguous handle range of the task table.
+ * Phase 1 counts the rank's ready tasks per group into d_counts (device pointer, n_groups_cap u32).
+ * The host all-gathers the count vectors (NCCL), then phase 2 runs the replicated deterministic solve
+ * on the summed counts and emits only this rank's tasks; ranks_before = element-wise sum of the count
+ * vectors of lower ranks, counts_all = sum over all ranks (device pointers). */
+int hqs_shard_count(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
+                    const uint64_t* free_rw, const uint64_t* total_rw, const uint8_t* blocked_wcv,
+                    uint32_t* d_counts, uint32_t n_groups_cap, uint32_t* n_groups);
+int hqs_shard_solve_emit(hqs_ctx* ctx, const uint32_t* d_counts_all, const uint32_t* d_ranks_before,
+                         uint32_t out_cap);
+/* Device pointer / length of the last tick's assignment buffer (for NCCL all-gather of results). */
+int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n);
+
+/* Restores every task that earlier ticks assigned (DONE) to the ready state (benchmark and what-if use:
+ * re-arm the same ready set without a new upload). */
+int hqs_ready_rearm(hqs_ctx* ctx);
+
+void* hqs_stream(hqs_ctx* ctx);                 /* cudaStream_t of the context                */
+/* Makes the context enqueue its work on an externally owned stream (e.g. the host framework's current
+ * stream) so that several contexts serialise on one stream and foreign events can time them. */
+int hqs_set_stream(hqs_ctx* ctx, void* cuda_stream);
+/* Per-kernel device timing of the tick (CUDA events on the context stream, off by default).
+ * out_ms[0..2] = count_k, solve_k, emit_k of the last fetched/synchronised tick, out_ms[3] = their sum. */
+int hqs_set_profile(hqs_ctx* ctx, int on);
+int hqs_get_kernel_ms(hqs_ctx* ctx, float out_ms[4]);
+int hqs_sync(hqs_ctx* ctx);
+int hqs_get_stats(hqs_ctx* ctx, hqs_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HQSCHED_H */

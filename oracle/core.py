@@ -163,10 +163,12 @@ class Core:
         return True
 
     # the tick ---------------------------------------------------------------------------------
-    def schedule_mapping(self, now: float = 0.0, time_limit: Optional[float] = None) -> WorkerTaskMapping:
+    def schedule_mapping(self, now: float = 0.0, time_limit: Optional[float] = None,
+                         mip_rel_gap: Optional[float] = None, accept_incumbent: bool = False) -> WorkerTaskMapping:
         """run_scheduling_inner minus send_messages (main.rs:40-46, env.rs:257-261)."""
         batches = create_task_batches(self, now)
-        solution = run_scheduling_solver(self, now, batches, time_limit=time_limit)
+        solution = run_scheduling_solver(self, now, batches, time_limit=time_limit, mip_rel_gap=mip_rel_gap,
+                                         accept_incumbent=accept_incumbent)
         self.last_solution = solution
         return create_task_mapping(self, solution)
 

@@ -69,8 +69,16 @@ class LpSolver:
         self.row_hi.append(hi)
 
     # solve --------------------------------------------------------------------------------
-    def solve(self, time_limit: Optional[float] = None) -> Optional[Tuple[np.ndarray, float]]:
-        """Maximise.  Returns (values, objective) or None unless the status is Optimal."""
+    def solve(self, time_limit: Optional[float] = None, mip_rel_gap: Optional[float] = None,
+              accept_incumbent: bool = False) -> Optional[Tuple[np.ndarray, float]]:
+        """Maximise.  Returns (values, objective) or None unless the status is Optimal.
+
+        Defaults reproduce the reference (HiGHS defaults, Optimal only).  The two relaxations exist
+        because the reference's MILP is a multi-dimensional knapsack that HiGHS cannot close to its
+        default 0.01 % gap in bounded time on many-class inputs (seconds to minutes for ~130 variables,
+        see DESIGN.md "oracle practicality"): `mip_rel_gap` loosens the optimality tolerance and
+        `accept_incumbent` returns the best feasible point when `time_limit` strikes (where the
+        reference would return None and schedule nothing, solver.rs:412-415)."""
         n = len(self.obj)
         if n == 0:
             return np.zeros(0), 0.0
@@ -82,8 +90,13 @@ class LpSolver:
         options = {"disp": False}
         if time_limit is not None:
             options["time_limit"] = time_limit
+        if mip_rel_gap is not None:
+            options["mip_rel_gap"] = mip_rel_gap
         res = milp(c, constraints=constraints, integrality=np.asarray(self.integrality),
                    bounds=Bounds(np.asarray(self.lb), np.asarray(self.ub)), options=options)
-        if res.status != 0 or res.x is None:        # 0 = optimal (HighsModelStatus::Optimal)
+        self.last_status = res.status
+        if res.x is None:
+            return None
+        if res.status != 0 and not (accept_incumbent and res.status == 1):   # 0 = Optimal, 1 = limit reached
             return None
         return res.x, -float(res.fun)

@@ -65,7 +65,8 @@ def _add_min_utilization(lp: LpSolver, worker, cpu_terms: List[Tuple[int, float]
 
 def run_scheduling_solver(core, now: float, batches: Sequence[TaskBatch],
                           custom_workers: Optional[Sequence] = None,
-                          time_limit: Optional[float] = None) -> SchedulingSolution:
+                          time_limit: Optional[float] = None, mip_rel_gap: Optional[float] = None,
+                          accept_incumbent: bool = False) -> SchedulingSolution:
     result = SchedulingSolution()
     if core.rq_map.is_empty():
         return result
@@ -191,7 +192,7 @@ def run_scheduling_solver(core, now: float, batches: Sequence[TaskBatch],
 
     result.n_vars = len(lp.obj)
     result.n_rows = len(lp.row_lo)
-    sol = lp.solve(time_limit=time_limit)
+    sol = lp.solve(time_limit=time_limit, mip_rel_gap=mip_rel_gap, accept_incumbent=accept_incumbent)
     if sol is None:
         result.solved = False        # non-optimal => empty solution, nothing scheduled (solver.rs:412-415)
         return result

@@ -1,0 +1,47 @@
+"""Generates tests/golden/oracle_drains.json: zero-duration drain makespans (tick counts) of the ORACLE
+(restated reference tick, HiGHS 1.12.0) on seeded synthetic workloads, plus the tick count of the current
+device algorithm's sequential specification (pins known gaps so they can only shrink).
+
+Run from the repo root:  python tests/golden/make_oracle_drains.py
+Oracle solver settings: parity.ORACLE_FAST (1 % MIP gap, 2 s cap, incumbent accepted) — see oracle/lp.py.
+"""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import greedy_model as G  # noqa: E402
+import parity as P  # noqa: E402
+
+CASES = {
+    "indep_4000_8_6_0": ("indep", [4000, 8, 6, 0], {}),
+    "indep_8000_16_8_1": ("indep", [8000, 16, 8, 1], {}),
+    "indep_6000_12_12_5": ("indep", [6000, 12, 12, 5], {}),
+    "indep_8000_16_16_2": ("indep", [8000, 16, 16, 2], {}),
+    "indep3_3000_8_6_3": ("indep", [3000, 8, 6, 3], {"variants3": True}),
+    "dag_6000_8_6_4": ("dag", [6000, 8, 6, 4], {"window": 512}),
+}
+
+out = {}
+path = os.path.join(HERE, "oracle_drains.json")
+if os.path.exists(path):
+    out = json.load(open(path))
+only = sys.argv[1:]
+for key, (kind, args, kwargs) in CASES.items():
+    if only and key not in only:
+        continue
+    wl = (P.make_dag if kind == "dag" else P.make_independent)(*args, **kwargs)
+    t0 = time.time()
+    if "--model-only" in sys.argv and key in out:
+        oracle_ticks, per_tick = out[key]["oracle_ticks"], None
+    else:
+        oracle_ticks, per_tick = P.oracle_drain(wl)
+    model_ticks, _ = G.model_drain(wl)
+    out[key] = {"args": args, "kwargs": kwargs, "oracle_ticks": oracle_ticks, "max_ticks": model_ticks,
+                "oracle_seconds": round(time.time() - t0, 1), "workload": wl.name}
+    print(key, out[key], flush=True)
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)

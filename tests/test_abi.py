@@ -1,0 +1,72 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/hqsched.h declares, struct layouts match the header, and — with no CUDA device — fails loudly
+instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from hyperqueue_b200 import _lib
+    return _lib.load_library()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "hqsched.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hqs_[a-z_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    from hyperqueue_b200 import _lib
+    assert declared == set(_lib.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hqs_abi_version() == 1
+
+
+def test_struct_layouts():
+    from hyperqueue_b200 import _lib
+    assert C.sizeof(_lib.hqs_variant) == 16 * 8 + 16
+    assert C.sizeof(_lib.hqs_class) == 8 + 8 * C.sizeof(_lib.hqs_variant)
+    assert C.sizeof(_lib.hqs_worker) == 24 == _lib.worker_dtype.itemsize
+    assert _lib.assignment_dtype.itemsize == 8
+    assert _lib.assignment_dtype.fields["worker"][1] == 4 and _lib.assignment_dtype.fields["variant"][1] == 6
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    ctx = C.c_void_p()
+    rc = lib.hqs_create(C.byref(ctx), 0, 4, 0)
+    assert rc == -2 and not ctx.value                       # HQS_E_CUDA
+    assert b"no CPU fallback" in lib.hqs_last_error(None)
+    from hyperqueue_b200 import GpuScheduler, HqsError
+    with pytest.raises(HqsError):
+        GpuScheduler(4)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hyperqueue_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "greedy_model" not in src, f
+
+
+def test_priority_mapping_matches_oracle():
+    from hyperqueue_b200 import priority_from_user
+    from oracle.model import priority_from_user as ref
+    ups = np.array([-2**31, -5, -1, 0, 1, 7, 123, 2**31 - 1])
+    got = priority_from_user(ups)
+    assert [int(x) for x in got] == [ref(int(u)) for u in ups]
+    assert (np.diff(got.astype(np.float64)) > 0).all()
