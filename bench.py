@@ -66,13 +66,13 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.sm_max = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self) -> None:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -84,10 +84,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}

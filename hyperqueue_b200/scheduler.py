@@ -234,10 +234,10 @@ class GpuScheduler:
     def _worker_structs(self, now: float) -> np.ndarray:
         w = np.zeros(self.worker_ids.shape[0], dtype=L.worker_dtype)
         w["worker_id"] = self.worker_ids
-        rem = np.where(np.isinf(self.termination), np.float64(L.HQS_TIME_INF),
-                       np.maximum(self.termination - now, 0.0) * 1000.0)
-        w["remaining_time_ms"] = np.where(np.isinf(self.termination), np.uint64(L.HQS_TIME_INF),
-                                          rem.astype(np.uint64))
+        finite = ~np.isinf(self.termination)
+        rem = np.full(self.termination.shape[0], L.HQS_TIME_INF, dtype=np.uint64)
+        rem[finite] = (np.maximum(self.termination[finite] - now, 0.0) * 1000.0).astype(np.uint64)
+        w["remaining_time_ms"] = rem
         w["min_utilization"] = self.min_utilization
         return w
 
