@@ -46,9 +46,8 @@ constexpr u32 KEY_LEVEL_SHIFT = 14;
 constexpr u32 KEY_LEVEL_MASK = 0x7FFFu;
 constexpr u32 KEY_CLASS_MASK = 0x3FFFu;
 
-constexpr u32 EMIT_WARPS = 8;             // warps per CTA in count_k / emit_k
-constexpr u32 EMIT_THREADS = EMIT_WARPS * 32;
-constexpr u32 CHUNK_ALIGN = EMIT_THREADS; // chunk size granularity (every warp gets whole 32-task rows)
+constexpr u32 COUNT_THREADS = 1024;       // count_k: one uint4 (4 tasks) per thread and pass
+constexpr u32 EMIT_SMEM_BUDGET = 96 * 1024;
 constexpr u32 SEG_CAP = 1u << 20;         // (group, worker, variant) count segments per tick
 constexpr u32 NEWPRIO_CAP = 4096;
 
@@ -63,24 +62,11 @@ struct __align__(16) GroupOut {
     u32 seg_n;    // number of count segments
 };
 
-// Device-side variant: dense amounts for the context's R resources.
-struct DevVariant {
-    u64 amount[HQS_MAX_RESOURCES];
-    u64 min_time_ms;
-    u32 all_mask;
-    u32 used_mask;  // bit r: amount[r] != 0 or all_mask bit r
-};
-struct DevClass {
-    u32 n_variants;
-    u32 pad;
-    DevVariant v[HQS_MAX_VARIANTS];
-};
-
 struct TickHeaderOut {
     u32 n_assigned;  // local assignments
     u32 n_groups;
     u32 n_segments;
-    u32 error;       // 1 = segment overflow
+    u32 error;       // 1 = segment overflow, 2 = solver grid synchronisation timed out
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -188,9 +174,9 @@ __global__ void finished_k(u32 n, const u32* __restrict__ task, const u32* __res
 
 // ------------------------------------------------------------------------------------------------
 // K1: count_k — histogram of ready tasks per group for one chunk of the task table.
-// HBM traffic: 4 B read per table slot.  smem: G u32 counters.
+// HBM traffic: 4 B read per table slot.  smem: G u32 counters.  One uint4 (4 tasks) per thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EMIT_THREADS)
+__global__ void __launch_bounds__(1024)
 count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32* __restrict__ table,
         u32* __restrict__ total) {
     extern __shared__ u32 s_hist[];
@@ -234,41 +220,305 @@ count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: solve_k.  CTA 0: first-fit solver.  CTAs >= 1: exclusive scan of table[][g] over chunks.
+// K2: solve_k (cooperative launch).
+//   CTA 0          sequential priority-ordered first-fit, one thread per worker (solve_body)
+//   CTAs 1..S      exclusive scan of table[][g] over chunks, one warp per group column
+//   CTAs >= 1      then wait for CTA 0: if the tick has a saturated level, every worker is filled by its
+//                  own warp (pack_body, alignment heuristic) spread over the whole grid
 // ------------------------------------------------------------------------------------------------
-struct SolveArgs {
-    // tick input (device copy of the host staging buffer)
-    const u64* free_rw;    // [W][R]
-    const u64* total_rw;   // [W][R]
-    const u64* rem_time;   // [W]
-    const u32* order;      // [Q] class ids in processing order inside one priority level
-    const uint8_t* blocked;  // [W][Q] bytes (bit v) or nullptr
-    const DevClass* classes;
-    u32 W, Q, L, R, G;
-    // counts
-    u32* total_local;      // [G] counts of this rank (zeroed here for the next tick)
-    const u32* total_all;  // [G] counts summed over ranks (== total_local when not sharded)
-    const u32* before;     // [G] counts of lower ranks, or nullptr
-    // outputs
-    GroupOut* gout;        // [G]
-    u32* seg_cum;          // [SEG_CAP] inclusive end rank of the segment inside its group
-    u32* seg_wv;           // [SEG_CAP] worker | variant << 16
-    u64* free_after;       // [W][R]
-    TickHeaderOut* hdr;
-    u32* glist;            // [G] scratch: non-empty groups in processing order
-    // scan part
-    u32* table;            // [P][G]
-    u32 P;
-};
+constexpr u32 PACK_MAX_CAND = 64;    // (class, variant) candidates of the packed level: 2 per lane
+constexpr u32 PACK_MAX_ITER = 64;
+constexpr u32 PACK_CHUNK_DIV = 8;
+constexpr u32 PHASE_WAIT = 0, PHASE_PACK = 1, PHASE_EXIT = 2;
+constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: a stuck grid must not hang the GPU
 
 template <int RT>
-__device__ void solve_body(const SolveArgs& a) {
-    __shared__ u64 s_wsum[32];
+struct VarT {
+    u64 amount[RT];
+    double rcp[RT];      // 1.0 / amount (0 where unused): floor(free / amount) without a 64-bit divide
+    u64 min_time_ms;
+    u32 all_mask;
+    u32 used_mask;
+};
+template <int RT>
+struct ClassT {
+    u32 n_variants;
+    u32 pad;
+    VarT<RT> v[HQS_MAX_VARIANTS];
+};
+
+struct SolveSync {
+    u32 phase;
+    u32 done;
+};
+
+struct PackScratch {          // global memory, written by CTA 0, read by the pack warps (and back)
+    u64* fr;                  // [W][R]
+    u32* quota;               // [W][PACK_MAX_CAND]   per (worker, group of the level)
+    u32* taken;               // [W][PACK_MAX_CAND]   per (worker, candidate)
+    u32* cand;                // [PACK_MAX_CAND]      class | variant << 16 | group-in-level << 24
+    u32* meta;                // [2] n_cand, n_groups
+};
+
+struct SolveArgs {
+    // tick input (device copy of the host staging buffer)
+    const u64* free_rw;      // [W][R]
+    const u64* total_rw;     // [W][R]
+    const u64* rem_time;     // [W]
+    const u32* order;        // [Q] class ids in processing order inside one priority level
+    const uint8_t* vorder;   // [Q][HQS_MAX_VARIANTS] variant ids in first-fit order
+    const uint8_t* blocked;  // [W][Q] bytes (bit v) or nullptr
+    const void* classes;     // ClassT<RT>[Q]
+    u32 W, Q, L, R, G;
+    u32 classes_bytes;       // Q * sizeof(ClassT<RT>)
+    u32 smem_classes;        // 1: stage the class table in shared memory
+    u32 pack_enabled;
+    // counts
+    u32* total_local;        // [G] counts of this rank (zeroed here for the next tick)
+    const u32* total_all;    // [G] counts summed over ranks (== total_local when not sharded)
+    const u32* before;       // [G] counts of lower ranks, or nullptr
+    // outputs
+    GroupOut* gout;          // [G]
+    u32* seg_cum;            // [SEG_CAP] inclusive end rank of the segment inside its group
+    u32* seg_wv;             // [SEG_CAP] worker | variant << 16
+    u64* free_after;         // [W][R]
+    TickHeaderOut* hdr;
+    uint2* glist;            // [G] scratch: non-empty groups (g, count) in processing order
+    // scan part
+    u32* table;              // [P][G]
+    u32 P;
+    u32 scan_ctas;
+    // pack part
+    SolveSync* sync;
+    PackScratch pk;
+};
+
+__device__ __forceinline__ u32 ld_acquire(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(u32* p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// floor(n / d) for d > 0 with the precomputed reciprocal; exact (the estimate is off by at most one)
+__device__ __forceinline__ u64 div_floor(u64 n, u64 d, double rcp) {
+    if (n >> 53) return n / d;
+    u64 q = (u64)__double2ull_rz(__dmul_rn(__ull2double_rn(n), rcp));
+    const u64 p = q * d;
+    if (p > n) --q;
+    else if (n - p >= d) ++q;
+    return q;
+}
+
+template <int RT>
+__device__ __forceinline__ bool admissible(const VarT<RT>& dv, u32 v, uint8_t blk, u64 rem_time) {
+    return !((blk >> v) & 1) && (rem_time == HQS_TIME_INF || dv.min_time_ms <= rem_time);
+}
+
+// how many tasks of the variant fit into `fr` now, at most `cap` (workerload.rs:121-145 without the 1024
+// cap; `All`: feasible with >= 1 fraction (request.rs:34-36) but consumes the total (solver.rs:120-124),
+// so at most one task and only on an untouched resource)
+template <int RT>
+__device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[RT], const VarT<RT>& dv, u64 cap) {
+    u64 cnt = cap;
+    const u32 used = dv.used_mask, allm = dv.all_mask;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        if (!((used >> r) & 1)) continue;
+        u64 q;
+        if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
+        else if (fr[r] != HQS_AMOUNT_MAX) q = div_floor(fr[r], dv.amount[r], dv.rcp[r]);
+        else continue;
+        cnt = cnt < q ? cnt : q;
+    }
+    return cnt;
+}
+
+template <int RT>
+__device__ __forceinline__ void take_from(u64 (&fr)[RT], const VarT<RT>& dv, u64 k) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        if (!((dv.used_mask >> r) & 1)) continue;
+        if ((dv.all_mask >> r) & 1) fr[r] = 0;                               // workerload.rs:162
+        else if (fr[r] != HQS_AMOUNT_MAX) fr[r] -= k * dv.amount[r];
+    }
+}
+
+// ---- pack: one warp fills one worker (specification: tests/greedy_model.py::_pack_level step b) ----
+template <int RT>
+__device__ void pack_body(const SolveArgs& a) {
+    const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n_pack_ctas = gridDim.x - 1;
+    const u32 n_cand = __ldcg(a.pk.meta);
+    // worker w is filled by CTA 1 + w % n_pack_ctas, warp w / n_pack_ctas: spreads the warps over the SMs
+    for (u32 w = (blockIdx.x - 1) + warp * n_pack_ctas; w < a.W; w += n_pack_ctas * (blockDim.x >> 5)) {
+        u64 fr[RT], tot[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            fr[r] = r < (int)a.R ? __ldcg(a.pk.fr + (size_t)w * a.R + r) : 0;
+            tot[r] = r < (int)a.R ? a.total_rw[(size_t)w * a.R + r] : 0;
+        }
+        const u64 rem_time = a.rem_time[w];
+        // my two candidates
+        u32 cls[2], var[2], gi[2], quota[2], taken[2];
+        bool live[2];
+        double norm[2];
+        const VarT<RT>* dv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const u32 ci = lane + 32 * j;
+            live[j] = ci < n_cand;
+            taken[j] = 0; quota[j] = 0; norm[j] = 0.0; cls[j] = var[j] = gi[j] = 0; dv[j] = &classes[0].v[0];
+            if (live[j]) {
+                const u32 cd = __ldcg(a.pk.cand + ci);
+                cls[j] = cd & 0xFFFFu; var[j] = (cd >> 16) & 0xFFu; gi[j] = cd >> 24;
+                dv[j] = &classes[cls[j]].v[var[j]];
+                quota[j] = __ldcg(a.pk.quota + (size_t)w * PACK_MAX_CAND + gi[j]);
+                const uint8_t blk = a.blocked ? a.blocked[(size_t)w * a.Q + cls[j]] : 0;
+                live[j] = admissible(*dv[j], var[j], blk, rem_time);
+                double s2 = 0.0;
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    double d = 0.0;
+                    if (((dv[j]->used_mask >> r) & 1) && tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX)
+                        d = __ddiv_rn(__ull2double_rn(dv[j]->amount[r]), __ull2double_rn(tot[r]));
+                    s2 = __dadd_rn(s2, __dmul_rn(d, d));
+                }
+                norm[j] = __dsqrt_rn(s2);
+            }
+        }
+        for (u32 it = 0; it < PACK_MAX_ITER; ++it) {
+            double u[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                u[r] = (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX) ? __ddiv_rn(__ull2double_rn(fr[r]), __ull2double_rn(tot[r])) : 0.0;
+            double best_s = 0.0;
+            u32 best_ci = ~0u;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (!live[j] || quota[j] == 0) continue;
+                bool fits = true;
+                double dot = 0.0;
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    double d = 0.0;
+                    if ((dv[j]->used_mask >> r) & 1) {
+                        if (fr[r] != HQS_AMOUNT_MAX && dv[j]->amount[r] > fr[r]) fits = false;
+                        if (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX)
+                            d = __ddiv_rn(__ull2double_rn(dv[j]->amount[r]), __ull2double_rn(tot[r]));
+                    }
+                    dot = __dadd_rn(dot, __dmul_rn(d, u[r]));
+                }
+                if (!fits) continue;
+                const double s = norm[j] > 0.0 ? __ddiv_rn(dot, norm[j]) : 0.0;
+                const u32 ci = lane + 32 * j;
+                if (best_ci == ~0u || s > best_s) { best_s = s; best_ci = ci; }   // j = 0 first: lower index wins ties
+            }
+            // warp argmax: larger score, ties to the lower candidate index
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double os = __shfl_xor_sync(0xffffffffu, best_s, d);
+                const u32 oc = __shfl_xor_sync(0xffffffffu, best_ci, d);
+                if (oc != ~0u && (best_ci == ~0u || os > best_s || (os == best_s && oc < best_ci))) { best_s = os; best_ci = oc; }
+            }
+            if (best_ci == ~0u) break;
+            const u32 owner = best_ci & 31, oj = best_ci >> 5;
+            u32 k = 0, ggi = 0;
+            const VarT<RT>* mydv = oj ? dv[1] : dv[0];
+            if (lane == owner) {
+                const u32 q = oj ? quota[1] : quota[0];
+                const u64 f = fit_count<RT>(fr, tot, *mydv, q);
+                const u32 chunk = q / PACK_CHUNK_DIV > 1 ? q / PACK_CHUNK_DIV : 1;
+                k = (u32)(f < chunk ? f : chunk);
+                if (oj) taken[1] += k; else taken[0] += k;
+                ggi = oj ? gi[1] : gi[0];
+            }
+            k = __shfl_sync(0xffffffffu, k, owner);
+            ggi = __shfl_sync(0xffffffffu, ggi, owner);
+            // every lane applies the owner's amounts to its copy of the free vector
+            const VarT<RT>* odv = (const VarT<RT>*)__shfl_sync(0xffffffffu, (unsigned long long)mydv, owner);
+            take_from<RT>(fr, *odv, k);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (gi[j] == ggi && (lane + 32 * j) < n_cand) quota[j] = quota[j] >= k ? quota[j] - k : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (lane + 32 * j < n_cand) a.pk.taken[(size_t)w * PACK_MAX_CAND + lane + 32 * j] = taken[j];
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                if (r < (int)a.R) a.pk.fr[(size_t)w * a.R + r] = fr[r];
+        }
+    }
+}
+
+// ---- CTA 0 ---------------------------------------------------------------------------------------
+struct ScanOut {
+    u32 take, exc_cnt, n_takers;
+    u64 tot_cnt;
+};
+
+// Block-wide "hand out `remaining` units in worker order": thread (worker) w offers cnt, receives
+// take = clamp(remaining - sum_{w' < w} cnt_{w'}, 0, cnt).  One barrier (double-buffered exchange).
+__device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u32& parity, u32& seg_rank) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    u64* buf = s_x + 32 * (parity & 1);
+    parity++;
+    const u64 x = cnt | (cnt ? (1ull << 42) : 0ull);     // low 42 bits count, high bits "has any"
+    u64 inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((int)lane >= d) inc += y;
+    }
+    if (lane == 31) buf[warp] = inc;
+    __syncthreads();
+    u64 winc = lane < nwarps ? buf[lane] : 0;            // every warp scans the warp totals itself
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 y = __shfl_up_sync(0xffffffffu, winc, d);
+        if ((int)lane >= d) winc += y;
+    }
+    const u64 block_total = __shfl_sync(0xffffffffu, winc, 31);
+    const u64 warp_off = warp ? __shfl_sync(0xffffffffu, winc, warp - 1) : 0;
+    const u64 exc = warp_off + inc - x;
+    const u64 mask = (1ull << 42) - 1;
+    ScanOut o;
+    o.exc_cnt = (u32)((exc & mask) < remaining ? (exc & mask) : remaining);
+    o.take = 0;
+    if (cnt && (exc & mask) < remaining) {
+        const u64 room = remaining - (exc & mask);
+        o.take = (u32)(cnt < room ? cnt : room);
+    }
+    seg_rank = (u32)(exc >> 42);
+    o.tot_cnt = block_total & mask;
+    o.n_takers = 0;      // the caller counts the takers (a second barrier that also fences s_x reuse)
+    return o;
+}
+
+template <int RT>
+__device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
+    __shared__ u64 s_x[64];
+    __shared__ u32 s_a[40], s_b[40];
     __shared__ u32 s_nlist;
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31, warp = tid >> 5;
     const u32 nwarps = blockDim.x >> 5;
     const bool has_worker = tid < a.W;
+    u32 parity = 0;
+
+    // ---- class table: shared memory when it fits, else global (uniform loads)
+    const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
+    if (a.smem_classes) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.classes);
+        uint4* dst = reinterpret_cast<uint4*>(smem_dyn);
+        for (u32 i = tid; i < a.classes_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        classes = reinterpret_cast<const ClassT<RT>*>(smem_dyn);
+    }
 
     u64 fr[RT], tot[RT];
 #pragma unroll
@@ -285,23 +535,22 @@ __device__ void solve_body(const SolveArgs& a) {
     const u32 n_pos = a.L * a.Q;
     for (u32 base = 0; base < n_pos; base += blockDim.x) {
         const u32 pos = base + tid;
-        u32 g = 0;
-        bool nz = false;
+        u32 g = 0, n = 0;
         if (pos < n_pos) {
             const u32 lvl = pos / a.Q, j = pos - lvl * a.Q;
             g = lvl * a.Q + a.order[j];
-            nz = a.total_all[g] != 0;
+            n = a.total_all[g];
         }
-        const u32 bal = __ballot_sync(0xffffffffu, nz);
-        if (lane == 0) s_wsum[warp] = __popc(bal);
+        const u32 bal = __ballot_sync(0xffffffffu, n != 0);
+        if (lane == 0) s_a[warp] = __popc(bal);
         __syncthreads();
         u32 off = s_nlist;
-        for (u32 w2 = 0; w2 < warp; ++w2) off += (u32)s_wsum[w2];
-        if (nz) a.glist[off + __popc(bal & ((1u << lane) - 1))] = g;
+        for (u32 w2 = 0; w2 < warp; ++w2) off += s_a[w2];
+        if (n) a.glist[off + __popc(bal & ((1u << lane) - 1))] = make_uint2(g, n);
         __syncthreads();
         if (tid == 0) {
             u32 t = 0;
-            for (u32 w2 = 0; w2 < nwarps; ++w2) t += (u32)s_wsum[w2];
+            for (u32 w2 = 0; w2 < nwarps; ++w2) t += s_a[w2];
             s_nlist += t;
         }
         __syncthreads();
@@ -310,105 +559,212 @@ __device__ void solve_body(const SolveArgs& a) {
 
     u32 seg_base = 0;    // uniform across the CTA
     u32 out_base = 0;    // uniform: local output offset
-    bool seg_overflow = false;
+    bool seg_overflow = false, sync_timeout = false;
+    bool packed = a.pack_enabled == 0;
+    bool signalled = false;
 
-    for (u32 li = 0; li < n_list; ++li) {
-        const u32 g = a.glist[li];
-        const u32 c = g % a.Q;
-        const u32 n_all = a.total_all[g];
-        const DevClass* cl = a.classes + c;
-        const u32 nv = cl->n_variants;
-        u32 remaining = n_all;
-        const u32 seg_lo = seg_base;
-        const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
+    u32 li = 0;
+    while (li < n_list) {
+        // ---- one priority level: entries [li, lj)
+        const u32 lvl = a.glist[li].x / a.Q;
+        u32 lj = li + 1;
+        while (lj < n_list && a.glist[lj].x / a.Q == lvl) ++lj;
+        const u32 ng = lj - li;
+        bool level_packed = false;
 
-        for (u32 v = 0; v < nv && remaining > 0; ++v) {
-            const DevVariant* dv = &cl->v[v];
-            const u32 all_mask = dv->all_mask;
-            const u32 used_mask = dv->used_mask;
-            // ---- how many tasks of (c, v) fit on my worker now
-            u64 cnt = 0;
-            if (has_worker && !((blk >> v) & 1) && (rem_time == HQS_TIME_INF || dv->min_time_ms <= rem_time)) {
-                cnt = remaining;
+        if (!packed && ng <= PACK_MAX_CAND) {
+            // ---- is this level saturated?  demand (first variant of the tick's order) vs free, exact u64
+            u32 n_cand = 0;
+            bool has_all = false;
+            for (u32 e = li; e < lj; ++e) {
+                const u32 c = a.glist[e].x % a.Q;
+                n_cand += classes[c].n_variants;
+                for (u32 v = 0; v < classes[c].n_variants; ++v) has_all |= classes[c].v[v].all_mask != 0;
+            }
+            if (n_cand <= PACK_MAX_CAND && !has_all) {
+                bool saturated = false;
+                for (u32 r = 0; r < a.R; ++r) {
+                    // C_r = saturating sum of free over workers (MAX => unbounded)
+                    u64 x = 0;
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    if (!((used_mask >> r) & 1)) continue;
-                    if ((all_mask >> r) & 1) {
-                        // `All`: feasible with >= 1 fraction (request.rs:34-36) but consumes the total
-                        // (solver.rs:120-124) => at most one task, only on an untouched resource
-                        const u64 q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
-                        cnt = cnt < q ? cnt : q;
-                    } else if (fr[r] != HQS_AMOUNT_MAX) {
-                        const u64 q = fr[r] / dv->amount[r];
-                        cnt = cnt < q ? cnt : q;
+                    for (int rr = 0; rr < RT; ++rr) if (rr == (int)r) x = fr[rr];
+                    if (!has_worker) x = 0;
+                    bool inf = has_worker && x == HQS_AMOUNT_MAX;
+                    // warp then block reduction with saturation
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        const u64 y = __shfl_xor_sync(0xffffffffu, x, d);
+                        const u64 s = x + y;
+                        x = s < x ? HQS_AMOUNT_MAX : s;
                     }
+                    inf = __any_sync(0xffffffffu, inf);
+                    u64* buf = s_x + 32 * (parity & 1);
+                    parity++;
+                    if (lane == 0) buf[warp] = inf ? HQS_AMOUNT_MAX : x;
+                    __syncthreads();
+                    u64 C = 0;
+                    for (u32 w2 = 0; w2 < nwarps; ++w2) {
+                        const u64 y = buf[w2];
+                        const u64 s = C + y;
+                        C = (y == HQS_AMOUNT_MAX || s < C) ? HQS_AMOUNT_MAX : s;
+                        if (C == HQS_AMOUNT_MAX) break;
+                    }
+                    if (C == HQS_AMOUNT_MAX) continue;
+                    u64 D = 0;
+                    for (u32 e = li; e < lj && D != HQS_AMOUNT_MAX; ++e) {
+                        const u32 c = a.glist[e].x % a.Q;
+                        const VarT<RT>& dv = classes[c].v[a.vorder[c * HQS_MAX_VARIANTS]];
+                        u64 am = 0;
+#pragma unroll
+                        for (int rr = 0; rr < RT; ++rr) if (rr == (int)r) am = dv.amount[rr];
+                        const unsigned __int128 p = (unsigned __int128)a.glist[e].y * am;
+                        const u64 pm = p > (unsigned __int128)HQS_AMOUNT_MAX ? HQS_AMOUNT_MAX : (u64)p;
+                        const u64 s = D + pm;
+                        D = s < D ? HQS_AMOUNT_MAX : s;
+                    }
+                    if (D > C) saturated = true;
+                }
+                if (saturated) {
+                    // ---- a. quotas: share of each class proportional to how many fit on the worker alone
+                    for (u32 e = li; e < lj; ++e) {
+                        const u32 c = a.glist[e].x % a.Q, n = a.glist[e].y;
+                        const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
+                        u64 cn = 0;
+                        if (has_worker)
+                            for (u32 v = 0; v < classes[c].n_variants; ++v) {
+                                const VarT<RT>& dv = classes[c].v[v];
+                                if (!admissible(dv, v, blk, rem_time)) continue;
+                                const u64 f = fit_count<RT>(fr, tot, dv, n);
+                                cn = f > cn ? f : cn;
+                            }
+                        u64 x = cn;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                        u64* buf = s_x + 32 * (parity & 1);
+                        parity++;
+                        if (lane == 0) buf[warp] = x;
+                        __syncthreads();
+                        u64 T = 0;
+                        for (u32 w2 = 0; w2 < nwarps; ++w2) T += buf[w2];
+                        if (has_worker) {
+                            const u64 q = T ? ((u64)n * cn + T - 1) / T : 0;
+                            a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)] = (u32)q;
+                        }
+                    }
+                    // ---- b. publish the worker state and the candidate list, release the pack warps
+                    if (has_worker) {
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            if (r < (int)a.R) a.pk.fr[(size_t)tid * a.R + r] = fr[r];
+                    }
+                    if (tid == 0) {
+                        u32 ci = 0;
+                        for (u32 e = li; e < lj; ++e) {
+                            const u32 c = a.glist[e].x % a.Q;
+                            for (u32 v = 0; v < classes[c].n_variants; ++v) a.pk.cand[ci++] = c | (v << 16) | ((e - li) << 24);
+                        }
+                        a.pk.meta[0] = ci;
+                        a.pk.meta[1] = ng;
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 timed_out = 0;
+                        st_release(&a.sync->phase, PHASE_PACK);
+                        const long long t0 = clock64();
+                        while (ld_acquire(&a.sync->done) < gridDim.x - 1) {
+                            if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { timed_out = 1; break; }
+                            __nanosleep(64);
+                        }
+                        s_b[0] = timed_out;
+                    }
+                    __syncthreads();
+                    sync_timeout = s_b[0] == 1;
+                    signalled = true;
+                    if (has_worker) {
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            if (r < (int)a.R) fr[r] = __ldcg(a.pk.fr + (size_t)tid * a.R + r);
+                    }
+                    packed = true;
+                    level_packed = !sync_timeout;
                 }
             }
-            // ---- block-wide scan of (cnt, cnt>0) packed in one u64: low 42 bits count, high bits flag
-            u64 x = cnt | (cnt ? (1ull << 42) : 0ull);
-            u64 inc = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((int)lane >= d) inc += y;
-            }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            // every warp scans the warp totals redundantly (no second barrier needed for the offsets)
-            u64 wt = lane < nwarps ? s_wsum[lane] : 0;
-            u64 winc = wt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u64 y = __shfl_up_sync(0xffffffffu, winc, d);
-                if ((int)lane >= d) winc += y;
-            }
-            const u64 block_total = __shfl_sync(0xffffffffu, winc, 31);
-            const u64 warp_off = warp ? __shfl_sync(0xffffffffu, winc, warp - 1) : 0;
-            const u64 exc = warp_off + inc - x;
-            const u64 exc_cnt = exc & ((1ull << 42) - 1);
-            const u32 exc_flag = (u32)(exc >> 42);
-            u32 take = 0;
-            if (cnt && exc_cnt < remaining) {
-                const u64 room = remaining - exc_cnt;
-                take = (u32)(cnt < room ? cnt : room);
-            }
-            const u32 done_before = n_all - remaining;
-            if (take) {
-                const u32 si = seg_base + exc_flag;
-                if (si < SEG_CAP) {
-                    a.seg_cum[si] = done_before + (u32)exc_cnt + take;
-                    a.seg_wv[si] = tid | (v << 16);
-                }
-#pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    if (!((used_mask >> r) & 1)) continue;
-                    if ((all_mask >> r) & 1) fr[r] = 0;                              // workerload.rs:162
-                    else if (fr[r] != HQS_AMOUNT_MAX) fr[r] -= (u64)take * dv->amount[r];
-                }
-            }
-            const u32 n_takers = (u32)__syncthreads_count(take != 0);   // also fences s_wsum reuse
-            const u64 tot_cnt = block_total & ((1ull << 42) - 1);
-            const u32 taken = (u32)(tot_cnt < remaining ? tot_cnt : remaining);
-            remaining -= taken;
-            seg_base += n_takers;
-            if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
         }
 
-        const u32 k = n_all - remaining;
-        // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
-        const u32 bef = a.before ? a.before[g] : 0;
-        const u32 loc = a.total_local[g];
-        u32 k_loc = k > bef ? k - bef : 0;
-        k_loc = k_loc < loc ? k_loc : loc;
-        if (tid == 0) {
-            GroupOut go;
-            go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_base - seg_lo;
-            a.gout[g] = go;
+        // ---- the groups of the level, in order: cap what pack took, then first-fit the rest
+        u32 cand_base = 0;
+        for (u32 e = li; e < lj; ++e) {
+            const u32 g = a.glist[e].x, n_all = a.glist[e].y;
+            const u32 c = g % a.Q;
+            const u32 nv = classes[c].n_variants;
+            u32 remaining = n_all;
+            const u32 seg_lo = seg_base;
+            const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
+            if (level_packed) {
+                for (u32 v = 0; v < nv; ++v) {
+                    const u64 cnt = has_worker ? __ldcg(a.pk.taken + (size_t)tid * PACK_MAX_CAND + cand_base + v) : 0;
+                    u32 seg_rank;
+                    ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+                    const VarT<RT>& dv = classes[c].v[v];
+                    if (o.take) {
+                        const u32 si = seg_base + seg_rank;
+                        if (si < SEG_CAP) {
+                            a.seg_cum[si] = (n_all - remaining) + o.exc_cnt + o.take;
+                            a.seg_wv[si] = tid | (v << 16);
+                        }
+                    }
+                    if (cnt > o.take) {
+                        const u64 ex = cnt - o.take;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            if (((dv.used_mask >> r) & 1) && fr[r] != HQS_AMOUNT_MAX) fr[r] += ex * dv.amount[r];
+                    }
+                    const u32 n_takers = (u32)__syncthreads_count(o.take != 0);
+                    remaining -= (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
+                    seg_base += n_takers;
+                    if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+                }
+                cand_base += nv;
+            }
+            for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
+                const u32 v = a.vorder[c * HQS_MAX_VARIANTS + vi];
+                const VarT<RT>& dv = classes[c].v[v];
+                u64 cnt = 0;
+                if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, dv, remaining);
+                u32 seg_rank;
+                ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+                if (o.take) {
+                    const u32 si = seg_base + seg_rank;
+                    if (si < SEG_CAP) {
+                        a.seg_cum[si] = (n_all - remaining) + o.exc_cnt + o.take;
+                        a.seg_wv[si] = tid | (v << 16);
+                    }
+                    take_from<RT>(fr, dv, o.take);
+                }
+                const u32 n_takers = (u32)__syncthreads_count(o.take != 0);
+                remaining -= (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
+                seg_base += n_takers;
+                if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+            }
+            const u32 k = n_all - remaining;
+            // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
+            const u32 bef = a.before ? a.before[g] : 0;
+            const u32 loc = a.total_local[g];
+            u32 k_loc = k > bef ? k - bef : 0;
+            k_loc = k_loc < loc ? k_loc : loc;
+            if (tid == 0) {
+                GroupOut go;
+                go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_base - seg_lo;
+                a.gout[g] = go;
+            }
+            out_base += k_loc;
         }
-        out_base += k_loc;
+        li = lj;
     }
 
-    // ---- epilogue: header, free vectors after the tick, reset the local counters for the next tick
+    // ---- epilogue: let the other CTAs go, header, free vectors after the tick, reset the counters
+    if (tid == 0 && !signalled) st_release(&a.sync->phase, PHASE_EXIT);
     if (has_worker) {
 #pragma unroll
         for (int r = 0; r < RT; ++r)
@@ -418,7 +774,7 @@ __device__ void solve_body(const SolveArgs& a) {
         a.hdr->n_assigned = out_base;
         a.hdr->n_groups = n_list;
         a.hdr->n_segments = seg_base;
-        a.hdr->error = seg_overflow ? 1u : 0u;
+        a.hdr->error = sync_timeout ? 2u : (seg_overflow ? 1u : 0u);
     }
     __syncthreads();
     for (u32 g = tid; g < a.G; g += blockDim.x) a.total_local[g] = 0;
@@ -426,51 +782,86 @@ __device__ void solve_body(const SolveArgs& a) {
 
 template <int RT>
 __global__ void __launch_bounds__(1024) solve_k(SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
     if (blockIdx.x == 0) {
-        solve_body<RT>(a);
+        solve_body<RT>(a, smem_dyn);
         return;
     }
-    // exclusive scan over chunks, one thread per group column; rows are contiguous => coalesced
-    const u32 g = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    if (g >= a.G) return;
-    u32 run = 0;
-    u32* col = a.table + g;
-    u32 b = 0;
-    for (; b + 4 <= a.P; b += 4) {   // 4 independent loads in flight
-        const u32 v0 = col[(size_t)(b + 0) * a.G], v1 = col[(size_t)(b + 1) * a.G];
-        const u32 v2 = col[(size_t)(b + 2) * a.G], v3 = col[(size_t)(b + 3) * a.G];
-        col[(size_t)(b + 0) * a.G] = run; run += v0;
-        col[(size_t)(b + 1) * a.G] = run; run += v1;
-        col[(size_t)(b + 2) * a.G] = run; run += v2;
-        col[(size_t)(b + 3) * a.G] = run; run += v3;
+    // ---- exclusive scan over chunks: one warp per group column, 32 chunk rows per step
+    if (blockIdx.x <= a.scan_ctas) {
+        const u32 lane = threadIdx.x & 31;
+        const u32 nw = blockDim.x >> 5;
+        for (u32 g = (blockIdx.x - 1) * nw + (threadIdx.x >> 5); g < a.G; g += a.scan_ctas * nw) {
+            u32 carry = 0;
+            for (u32 b0 = 0; b0 < a.P; b0 += 32) {
+                const u32 b = b0 + lane;
+                const u32 v = b < a.P ? a.table[(size_t)b * a.G + g] : 0;
+                u32 inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                    if ((int)lane >= d) inc += y;
+                }
+                if (b < a.P) a.table[(size_t)b * a.G + g] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
     }
-    for (; b < a.P; ++b) {
-        const u32 v = col[(size_t)b * a.G];
-        col[(size_t)b * a.G] = run;
-        run += v;
+    // ---- wait for CTA 0's decision
+    __shared__ u32 s_cmd;
+    if (threadIdx.x == 0) {
+        u32 cmd;
+        const long long t0 = clock64();
+        while ((cmd = ld_acquire(&a.sync->phase)) == PHASE_WAIT) {
+            if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { cmd = PHASE_EXIT; break; }
+            __nanosleep(128);
+        }
+        s_cmd = cmd;
+    }
+    __syncthreads();
+    if (s_cmd == PHASE_PACK) {
+        pack_body<RT>(a);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&a.sync->done, 1u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K3: emit_k — stable (handle-ordered) rank of every ready task inside its group, rank -> placement.
 // Each warp owns a contiguous sub-chunk; per-warp group counters live in shared memory:
-//   s_cnt[w][g]  first pass: tasks of group g in warp w's sub-chunk; then turned into the global rank
-//                at which warp w's first task of group g starts; second pass: running counter.
+//   s_cnt[w][g]  first pass: tasks of group g in warp w's sub-chunk; then turned into the rank at which
+//                warp w's first task of group g starts; second pass: running counter.
+// The per-group solver output and (when they fit) the count segments are staged in shared memory.
 // HBM traffic: 4 B read per table slot (second read hits L1/L2), 8 B written per assignment, 4 B key
 // write-back per assignment.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EMIT_THREADS)
-emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, const u32* __restrict__ table,
+constexpr u32 EMIT_SEG_SMEM = 1024;
+
+__global__ void __launch_bounds__(1024)
+emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem, const u32* __restrict__ table,
        const u32* __restrict__ before, const GroupOut* __restrict__ gout, const u32* __restrict__ seg_cum,
-       const u32* __restrict__ seg_wv, hqs_assignment* __restrict__ out, u32 out_cap) {
-    extern __shared__ u32 s_cnt[];   // [EMIT_WARPS][G]
+       const u32* __restrict__ seg_wv, const TickHeaderOut* __restrict__ hdr, hqs_assignment* __restrict__ out,
+       u32 out_cap) {
+    extern __shared__ __align__(16) u32 s_emit[];
+    const u32 nwarps = blockDim.x >> 5;
+    u32* s_cnt = s_emit;                                              // [nwarps][G]
+    GroupOut* s_go = reinterpret_cast<GroupOut*>(s_emit + nwarps * G);  // [G] when g_smem
+    u32* s_segc = reinterpret_cast<u32*>(s_go + (g_smem ? G : 0));     // [EMIT_SEG_SMEM]
+    u32* s_segw = s_segc + EMIT_SEG_SMEM;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 i = threadIdx.x; i < EMIT_WARPS * G; i += blockDim.x) s_cnt[i] = 0;
+    for (u32 i = threadIdx.x; i < nwarps * G; i += blockDim.x) s_cnt[i] = 0;
+    const u32 n_seg = hdr->n_segments;
+    const bool seg_smem = n_seg <= EMIT_SEG_SMEM;
+    if (g_smem)
+        for (u32 g = threadIdx.x; g < G; g += blockDim.x) s_go[g] = gout[g];
+    if (seg_smem)
+        for (u32 i = threadIdx.x; i < n_seg; i += blockDim.x) { s_segc[i] = seg_cum[i]; s_segw[i] = seg_wv[i]; }
     __syncthreads();
 
     const u32 base = blockIdx.x * chunk;
     const u32 end = min(base + chunk, n_handles);
-    const u32 sub = chunk / EMIT_WARPS;              // multiple of 32
+    const u32 sub = chunk / nwarps;                  // multiple of 32
     const u32 wbeg = base + warp * sub;
     const u32 wend = min(wbeg + sub, end);
     u32* mycnt = s_cnt + warp * G;
@@ -488,12 +879,11 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, const u32*
         if (i - lane + 32 >= wend) break;   // uniform: whole row past the end
     }
     __syncthreads();
-    // turn counts into starting ranks: rank0(w, g) = before[g] + table[b][g] + sum_{w' < w} cnt[w'][g]
+    // turn counts into starting ranks: rank0(w, g) = table[b][g] + sum_{w' < w} cnt[w'][g]
     const u32* row = table + (size_t)blockIdx.x * G;
     for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
         u32 run = row[g];
-#pragma unroll
-        for (u32 w2 = 0; w2 < EMIT_WARPS; ++w2) {
+        for (u32 w2 = 0; w2 < nwarps; ++w2) {
             const u32 c = s_cnt[w2 * G + g];
             s_cnt[w2 * G + g] = run;
             run += c;
@@ -518,16 +908,25 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, const u32*
             r0 = __shfl_sync(peers, r0, leader);
             const u32 r_loc = r0 + __popc(peers & ((1u << lane) - 1));   // rank among this rank's tasks
             const u32 bef = before ? __ldg(before + g) : 0u;
-            const GroupOut go = gout[g];
+            const GroupOut go = g_smem ? s_go[g] : gout[g];
             if (r_loc + bef < go.k) {
                 const u32 r = r_loc + bef;                                // global rank in the group
                 // first segment whose inclusive end rank exceeds r
                 u32 lo = go.seg_lo, hi = go.seg_lo + go.seg_n;
-                while (lo < hi) {
-                    const u32 mid = (lo + hi) >> 1;
-                    if (__ldg(seg_cum + mid) > r) hi = mid; else lo = mid + 1;
+                u32 wv;
+                if (seg_smem) {
+                    while (lo < hi) {
+                        const u32 mid = (lo + hi) >> 1;
+                        if (s_segc[mid] > r) hi = mid; else lo = mid + 1;
+                    }
+                    wv = s_segw[lo];
+                } else {
+                    while (lo < hi) {
+                        const u32 mid = (lo + hi) >> 1;
+                        if (__ldg(seg_cum + mid) > r) hi = mid; else lo = mid + 1;
+                    }
+                    wv = __ldg(seg_wv + lo);
                 }
-                const u32 wv = __ldg(seg_wv + lo);
                 const u32 oi = go.out_off + r_loc;
                 if (oi < out_cap) {
                     hqs_assignment asg;
@@ -559,8 +958,10 @@ struct hqs_ctx {
     // classes
     u32 Q = 0;
     std::vector<hqs_class> classes;
-    DevClass* d_classes = nullptr;
-    u32 d_classes_cap = 0;
+    unsigned char* d_classes = nullptr;   // ClassT<RT>[Q]
+    u32 d_classes_cap = 0;                // bytes
+    u32 RT = 4;                           // resource slots of the device class layout (4, 8 or 16)
+    u32 class_bytes = 0;                  // sizeof(ClassT<RT>)
     // priority levels (descending)
     std::vector<u64> levels;      // exact distinct priorities seen, descending
     std::vector<u64> dev_levels;  // what the device uses (== levels, or bucket bounds when coarsened)
@@ -585,7 +986,9 @@ struct hqs_ctx {
     u32* d_table = nullptr;
     u32* d_total = nullptr;
     GroupOut* d_gout = nullptr;
-    u32* d_glist = nullptr;
+    uint2* d_glist = nullptr;
+    SolveSync* d_sync = nullptr;
+    u64* d_pk_fr = nullptr; u32* d_pk_quota = nullptr; u32* d_pk_taken = nullptr; u32* d_pk_cand = nullptr; u32* d_pk_meta = nullptr;
     u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr;
     hqs_assignment* d_out = nullptr; u32 out_cap_dev = 0;
     TickHeaderOut* d_hdr = nullptr;
@@ -600,6 +1003,7 @@ struct hqs_ctx {
     bool tick_pending = false;
     bool own_stream = true;
     bool profile = false;
+    bool pack = true;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     hqs_stats stats{};
@@ -748,7 +1152,7 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
             CU(cudaMemsetAsync(ctx->d_total, 0, ng * sizeof(u32), ctx->stream));
             CU(cudaMalloc(&ctx->d_gout, ng * sizeof(GroupOut)));
             CU(cudaMemsetAsync(ctx->d_gout, 0, ng * sizeof(GroupOut), ctx->stream));
-            CU(cudaMalloc(&ctx->d_glist, ng * sizeof(u32)));
+            CU(cudaMalloc(&ctx->d_glist, ng * sizeof(uint2)));
         }
         ctx->G_cap = ng; ctx->P_cap = np;
     }
@@ -757,6 +1161,12 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
         CU(cudaMalloc(&ctx->d_seg_wv, SEG_CAP * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_hdr, sizeof(TickHeaderOut)));
         CU(cudaMalloc(&ctx->d_free_after, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
+        CU(cudaMalloc(&ctx->d_sync, sizeof(SolveSync)));
+        CU(cudaMalloc(&ctx->d_pk_fr, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
+        CU(cudaMalloc(&ctx->d_pk_quota, (size_t)HQS_MAX_WORKERS * PACK_MAX_CAND * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_pk_taken, (size_t)HQS_MAX_WORKERS * PACK_MAX_CAND * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_pk_cand, PACK_MAX_CAND * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_pk_meta, 2 * sizeof(u32)));
     }
     if (out_cap > ctx->out_cap_dev) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -769,7 +1179,7 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
 }
 
 struct TickLayout {
-    size_t off_free, off_total, off_rem, off_order, off_blocked, bytes;
+    size_t off_free, off_total, off_rem, off_order, off_vorder, off_blocked, bytes;
 };
 
 TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
@@ -779,16 +1189,20 @@ TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
     l.off_total = o; o += (size_t)W * R * 8;
     l.off_rem = o; o += (size_t)W * 8;
     l.off_order = o; o += (size_t)Q * 4;
+    l.off_vorder = o; o += (size_t)Q * HQS_MAX_VARIANTS;
     o = (o + 15) & ~size_t(15);
     l.off_blocked = o; if (blocked) o += (size_t)W * Q;
     l.bytes = (o + 15) & ~size_t(15);
     return l;
 }
 
-// processing order of classes inside one priority level: descending objective weight of one task,
-// the greedy analogue of the MILP coefficient of create_sn_var (solver.rs:520-549):
-//   weight * sum_r amount_r / S_r,   S_r = sum over workers of free[r] (MAX counts as one unit)
-void class_order(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total_rw, u32* order) {
+// Per-tick orders, both from S_r = sum over workers of free[r] (MAX counts as one unit):
+//  order[]   classes inside one priority level by descending objective weight of one task, the greedy
+//            analogue of the MILP coefficient of create_sn_var (solver.rs:520-549):
+//            weight * sum_r amount_r / S_r
+//  vorder[]  variants of a class by ascending dominant share max_r amount_r / S_r: the variant that costs
+//            least of the scarcest thing it touches is tried first
+void tick_orders(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total_rw, u32* order, uint8_t* vorder) {
     const u32 R = ctx->R, Q = ctx->Q;
     double S[HQS_MAX_RESOURCES], T[HQS_MAX_RESOURCES];
     for (u32 r = 0; r < R; ++r) { S[r] = 0; T[r] = 0; }
@@ -803,17 +1217,29 @@ void class_order(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total
     for (u32 c = 0; c < Q; ++c) {
         double best = 0;
         const hqs_class& cl = ctx->classes[c];
+        std::pair<double, u32> doms[HQS_MAX_VARIANTS];
         for (u32 v = 0; v < cl.n_variants; ++v) {
-            double s = 0;
+            double s = 0, dom = 0;
             for (u32 r = 0; r < R; ++r) {
+                const bool all = (cl.variants[v].all_mask >> r) & 1;
+                const u64 amt = all ? 0 : cl.variants[v].amount[r];
+                if (amt) {
+                    const double x = S[r] < 1e-6 ? INFINITY : ((double)amt / 10000.0) / S[r];
+                    dom = x > dom ? x : dom;
+                }
                 if (S[r] < 1e-6) continue;
-                if ((cl.variants[v].all_mask >> r) & 1) s += (T[r] / std::max<u32>(W, 1)) / S[r];
-                else s += ((double)cl.variants[v].amount[r] / 10000.0) / S[r];
+                if (all) s += (T[r] / std::max<u32>(W, 1)) / S[r];
+                else s += ((double)amt / 10000.0) / S[r];
             }
+            if (cl.variants[v].all_mask) dom = INFINITY;
             s *= (double)cl.variants[v].weight / 10000.0;
             best = std::max(best, s);
+            doms[v] = {dom, v};
         }
         sc[c] = {best, c};
+        std::stable_sort(doms, doms + cl.n_variants,
+                         [](const std::pair<double, u32>& a, const std::pair<double, u32>& b) { return a.first < b.first; });
+        for (u32 v = 0; v < HQS_MAX_VARIANTS; ++v) vorder[c * HQS_MAX_VARIANTS + v] = v < cl.n_variants ? (uint8_t)doms[v].second : 0;
     }
     std::stable_sort(sc.begin(), sc.end(), [](const std::pair<double, u32>& a, const std::pair<double, u32>& b) {
         return a.first > b.first;
@@ -821,17 +1247,26 @@ void class_order(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total
     for (u32 c = 0; c < Q; ++c) order[c] = sc[c].second;
 }
 
-struct TickGeom { u32 G, L, P, chunk; };
+struct TickGeom { u32 G, L, P, chunk, emit_warps, g_smem; size_t emit_smem; };
 
 TickGeom tick_geom(const hqs_ctx* ctx) {
     TickGeom t;
     t.L = std::max<u32>((u32)ctx->dev_levels.size(), 1);
     t.G = t.L * std::max<u32>(ctx->Q, 1);
-    // shared memory of emit_k: EMIT_WARPS * G * 4 B; two CTAs per SM while that stays under ~100 KB
-    const u32 p_max = ((size_t)EMIT_WARPS * t.G * 4 <= 100 * 1024 ? 2u : 1u) * ctx->sm_count;
+    // emit_k shared memory: warps * G counters (+ G solver records + the segment cache); as many warps per
+    // CTA as the budget allows, two CTAs per SM
+    const size_t seg_cache = 2 * EMIT_SEG_SMEM * sizeof(u32);
+    t.emit_warps = 8;
+    for (u32 ew : {32u, 16u}) {
+        if ((size_t)ew * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= 64 * 1024) { t.emit_warps = ew; break; }
+    }
+    t.g_smem = ((size_t)t.emit_warps * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= EMIT_SMEM_BUDGET) ? 1 : 0;
+    t.emit_smem = (size_t)t.emit_warps * t.G * 4 + (t.g_smem ? (size_t)t.G * sizeof(GroupOut) : 0) + seg_cache;
+    const u32 align = 32 * t.emit_warps;
+    const u32 p_max = (t.emit_smem <= 100 * 1024 ? 2u : 1u) * ctx->sm_count;
     const u32 n = std::max<u32>(ctx->n_handles, 1);
     u32 chunk = (n + p_max - 1) / p_max;
-    chunk = std::max<u32>(CHUNK_ALIGN, (chunk + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN);
+    chunk = std::max<u32>(align, (chunk + align - 1) / align * align);
     t.chunk = chunk;
     t.P = (n + chunk - 1) / chunk;
     return t;
@@ -854,7 +1289,7 @@ int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64*
     memcpy(h + lay.off_total, total_rw, (size_t)W * R * 8);
     u64* rem = reinterpret_cast<u64*>(h + lay.off_rem);
     for (u32 w = 0; w < W; ++w) rem[w] = workers[w].remaining_time_ms;
-    class_order(ctx, W, free_rw, total_rw, reinterpret_cast<u32*>(h + lay.off_order));
+    tick_orders(ctx, W, free_rw, total_rw, reinterpret_cast<u32*>(h + lay.off_order), h + lay.off_vorder);
     if (blocked) {
         // ABI bit index ((w*Q + c) * HQS_MAX_VARIANTS + v) with HQS_MAX_VARIANTS == 8: one byte per (w, c)
         memcpy(h + lay.off_blocked, blocked, (size_t)W * Q);
@@ -877,7 +1312,7 @@ int validate_workers(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* 
 int launch_count(hqs_ctx* ctx, const TickGeom& t) {
     ctx->ev_valid = false;
     if (ctx->profile) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    count_k<<<t.P, EMIT_THREADS, t.G * sizeof(u32), ctx->stream>>>(ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G,
+    count_k<<<t.P, COUNT_THREADS, t.G * sizeof(u32), ctx->stream>>>(ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G,
                                                                    ctx->d_table, ctx->d_total);
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
@@ -892,9 +1327,12 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.total_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_total);
     a.rem_time = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_rem);
     a.order = reinterpret_cast<const u32*>(ctx->d_tickin + lay.off_order);
+    a.vorder = ctx->d_tickin + lay.off_vorder;
     a.blocked = blocked ? ctx->d_tickin + lay.off_blocked : nullptr;
     a.classes = ctx->d_classes;
     a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
+    a.classes_bytes = ctx->Q * ctx->class_bytes;
+    a.smem_classes = a.classes_bytes <= 64 * 1024 ? 1 : 0;
     a.total_local = ctx->d_total;
     a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
     a.before = d_before;
@@ -904,17 +1342,27 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.hdr = ctx->d_hdr;
     a.glist = ctx->d_glist;
     a.table = ctx->d_table; a.P = t.P;
-    const u32 threads = std::max<u32>(64, (W + 31) / 32 * 32);
-    const u32 scan_ctas = (t.G + threads - 1) / threads;
-    if (ctx->R <= 4) solve_k<4><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
-    else if (ctx->R <= 8) solve_k<8><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
-    else solve_k<16><<<1 + scan_ctas, threads, 0, ctx->stream>>>(a);
+    a.sync = ctx->d_sync;
+    a.pk.fr = ctx->d_pk_fr; a.pk.quota = ctx->d_pk_quota; a.pk.taken = ctx->d_pk_taken;
+    a.pk.cand = ctx->d_pk_cand; a.pk.meta = ctx->d_pk_meta;
+    const u32 threads = std::max<u32>(128, (W + 31) / 32 * 32);
+    const u32 nw = threads / 32;
+    a.scan_ctas = std::min<u32>((t.G + nw - 1) / nw, ctx->sm_count - 1);
+    // grid: CTA 0 solves; the others scan the chunk table and then stand by to fill workers (one warp per
+    // worker, spread over the SMs).  All CTAs must be co-resident (cooperative launch): <= one per SM.
+    u32 grid = std::max<u32>(1 + a.scan_ctas, std::min<u32>(ctx->sm_count, 1 + (W + 1) / 2));
+    grid = std::min<u32>(grid, ctx->sm_count);
+    a.pack_enabled = (ctx->pack && grid >= 2) ? 1 : 0;
+    const size_t solve_smem = a.smem_classes ? a.classes_bytes : 0;
+    CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
+    void* kargs[] = {&a};
+    const void* fn = ctx->RT == 4 ? (const void*)solve_k<4> : ctx->RT == 8 ? (const void*)solve_k<8> : (const void*)solve_k<16>;
+    CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
     ctx->stats.kernel_launches++;
-    CU(cudaGetLastError());
     if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    emit_k<<<t.P, EMIT_THREADS, (size_t)EMIT_WARPS * t.G * sizeof(u32), ctx->stream>>>(
-        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
-        ctx->d_seg_wv, ctx->d_out, out_cap);
+    emit_k<<<t.P, 32 * t.emit_warps, t.emit_smem, ctx->stream>>>(
+        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, t.g_smem, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
+        ctx->d_seg_wv, ctx->d_hdr, ctx->d_out, out_cap);
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
     if (ctx->profile) { CU(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid = true; }
@@ -937,7 +1385,6 @@ const char* hqs_last_error(const hqs_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) {
     hqs_ctx* ctx = nullptr;
-    (void)flags;
     if (!out) return fail(nullptr, HQS_E_INVALID, "out is null");
     *out = nullptr;
     if (n_resources == 0 || n_resources > HQS_MAX_RESOURCES)
@@ -952,6 +1399,9 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (!ctx) return fail(nullptr, HQS_E_NOMEM, "out of memory");
     ctx->device = device;
     ctx->R = n_resources;
+    ctx->RT = n_resources <= 4 ? 4 : n_resources <= 8 ? 8 : 16;
+    ctx->class_bytes = ctx->RT == 4 ? sizeof(ClassT<4>) : ctx->RT == 8 ? sizeof(ClassT<8>) : sizeof(ClassT<16>);
+    ctx->pack = !(flags & 1u);
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     int sms = 0;
@@ -959,8 +1409,10 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newcnt, sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(EMIT_WARPS * HQS_MAX_GROUPS * sizeof(u32)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete ctx;
@@ -978,7 +1430,8 @@ void hqs_destroy(hqs_ctx* ctx) {
     void* dev_ptrs[] = {ctx->d_classes, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
                         ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
                         ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_glist, ctx->d_seg_cum,
-                        ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin};
+                        ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
+                        ctx->d_pk_quota, ctx->d_pk_taken, ctx->d_pk_cand, ctx->d_pk_meta};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->h_tickin) cudaFreeHost(ctx->h_tickin);
     if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
@@ -992,40 +1445,50 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
     if (!ctx) return HQS_E_INVALID;
     if (!classes || n_classes == 0) return fail(ctx, HQS_E_INVALID, "empty class table");
     if (n_classes > HQS_MAX_CLASSES) return fail(ctx, HQS_E_LIMIT, "n_classes=%u > %u", n_classes, HQS_MAX_CLASSES);
-    std::vector<DevClass> dev(n_classes);
+    // device layout: ClassT<RT>[Q] with RT = 4 / 8 / 16 resource slots, built as raw bytes
+    const u32 RT = ctx->RT;
+    const size_t var_bytes = (size_t)RT * 16 + 16, cls_bytes = ctx->class_bytes;
+    std::vector<unsigned char> blob((size_t)n_classes * cls_bytes, 0);
     for (u32 c = 0; c < n_classes; ++c) {
-        const hqs_class& s = classes[c];
-        if (s.n_nodes != 0) return fail(ctx, HQS_E_INVALID, "class %u: multi-node requests are outside this path", c);
-        if (s.n_variants == 0 || s.n_variants > HQS_MAX_VARIANTS)
-            return fail(ctx, HQS_E_LIMIT, "class %u: n_variants=%u outside 1..%u", c, s.n_variants, HQS_MAX_VARIANTS);
-        DevClass& d = dev[c];
-        memset(&d, 0, sizeof d);
-        d.n_variants = s.n_variants;
-        for (u32 v = 0; v < s.n_variants; ++v) {
+        const hqs_class& sc = classes[c];
+        if (sc.n_nodes != 0) return fail(ctx, HQS_E_INVALID, "class %u: multi-node requests are outside this path", c);
+        if (sc.n_variants == 0 || sc.n_variants > HQS_MAX_VARIANTS)
+            return fail(ctx, HQS_E_LIMIT, "class %u: n_variants=%u outside 1..%u", c, sc.n_variants, HQS_MAX_VARIANTS);
+        unsigned char* cb = blob.data() + (size_t)c * cls_bytes;
+        memcpy(cb, &sc.n_variants, 4);
+        for (u32 v = 0; v < sc.n_variants; ++v) {
+            unsigned char* vb = cb + 8 + (size_t)v * var_bytes;
+            u64* amount = reinterpret_cast<u64*>(vb);
+            double* rcp = reinterpret_cast<double*>(vb + (size_t)RT * 8);
+            u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 16);
+            u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 16 + 8);
             u32 used = 0;
             for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) {
-                const bool all = (s.variants[v].all_mask >> r) & 1;
-                const u64 amt = s.variants[v].amount[r];
+                const bool all = (sc.variants[v].all_mask >> r) & 1;
+                const u64 amt = sc.variants[v].amount[r];
                 if ((all || amt) && r >= ctx->R)
                     return fail(ctx, HQS_E_INVALID, "class %u variant %u uses resource %u >= n_resources", c, v, r);
-                d.v[v].amount[r] = all ? 0 : amt;
+                if (r < RT) {
+                    amount[r] = all ? 0 : amt;
+                    rcp[r] = (!all && amt) ? 1.0 / (double)amt : 0.0;
+                }
                 if (all || amt) used |= 1u << r;
             }
             if (!used) return fail(ctx, HQS_E_INVALID, "class %u variant %u: empty request (request.rs:191-194)", c, v);
-            if (s.variants[v].weight == 0) return fail(ctx, HQS_E_INVALID, "class %u variant %u: zero weight", c, v);
-            d.v[v].all_mask = s.variants[v].all_mask & ((1u << ctx->R) - 1);
-            d.v[v].used_mask = used;
-            d.v[v].min_time_ms = s.variants[v].min_time_ms;
+            if (sc.variants[v].weight == 0) return fail(ctx, HQS_E_INVALID, "class %u variant %u: zero weight", c, v);
+            *min_time = sc.variants[v].min_time_ms;
+            masks[0] = sc.variants[v].all_mask & ((1u << ctx->R) - 1);
+            masks[1] = used;
         }
     }
     CU(cudaSetDevice(ctx->device));
-    if (n_classes > ctx->d_classes_cap) {
+    if (blob.size() > ctx->d_classes_cap) {
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_classes) CU(cudaFree(ctx->d_classes));
-        ctx->d_classes_cap = std::max<u32>(n_classes * 2, 16);
-        CU(cudaMalloc(&ctx->d_classes, ctx->d_classes_cap * sizeof(DevClass)));
+        ctx->d_classes_cap = (u32)std::max<size_t>(blob.size() * 2, 4096);
+        CU(cudaMalloc(&ctx->d_classes, ctx->d_classes_cap));
     }
-    CU(cudaMemcpyAsync(ctx->d_classes, dev.data(), n_classes * sizeof(DevClass), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_classes, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const bool q_changed = ctx->Q != n_classes;
     ctx->classes.assign(classes, classes + n_classes);
@@ -1244,6 +1707,7 @@ int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t
     ctx->stats.n_levels = ctx->last_L;
     ctx->stats.n_assigned = hdr.n_assigned;
     ctx->stats.n_segments = hdr.n_segments;
+    if (hdr.error == 2) return fail(ctx, HQS_E_CUDA, "solver grid synchronisation timed out");
     if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
     if (hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
         return fail(ctx, HQS_E_OVERFLOW, "out_cap=%u too small for %u assignments", out_cap, hdr.n_assigned);

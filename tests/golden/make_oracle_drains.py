@@ -30,7 +30,7 @@ out = {}
 path = os.path.join(HERE, "oracle_drains.json")
 if os.path.exists(path):
     out = json.load(open(path))
-only = sys.argv[1:]
+only = [a for a in sys.argv[1:] if not a.startswith('--')]
 for key, (kind, args, kwargs) in CASES.items():
     if only and key not in only:
         continue

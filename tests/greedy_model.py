@@ -1,13 +1,25 @@
-"""Sequential CPU model of the DEVICE algorithm (priority-ordered first-fit over (level, class) groups).
+"""Sequential CPU specification of the DEVICE algorithm (hyperqueue_b200/csrc/hqsched.cu).
 
 Test infrastructure: it is neither the oracle (which restates the reference's MILP) nor a product
 fallback.  It exists so that (a) the design can be compared with the oracle on the CPU-only box and
-(b) the CUDA path can be checked for bit-exact equality with a 60-line specification of itself.
-Mirrors hyperqueue_b200/csrc/hqsched.cu: class_order(), solve_body(), emit_k().
+(b) the CUDA path can be checked for bit-exact equality with a short specification of itself.
+
+The algorithm, per tick:
+  levels (distinct priorities, descending) x classes (the tick's class order) = groups; groups are
+  processed in that order.  The FIRST level whose demand exceeds the aggregate free capacity is
+  "packed": the level's class counts are pre-split over the workers (share proportional to how many
+  tasks of the class fit on the worker alone) and every worker then fills ITSELF, independently, by
+  repeatedly taking the candidate (class, variant) best aligned with its remaining capacity (normalised
+  dot product, the vector-bin-packing heuristic) — this is what makes one tick use cpus, gpus and memory
+  together the way the reference's MILP objective (sum of normalised utilisations, solver.rs:520-549)
+  does.  Everything else — levels before and after, and whatever the packed level could not place — is
+  priority-ordered first-fit over workers in ascending id (compaction, solver.rs (n - w_idx)/n).
+Mirrors class_order(), solve_body() / pack_body(), emit_k().
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import math
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -15,6 +27,10 @@ from parity import FR, MAXV, Workload
 
 AMOUNT_MAX = (1 << 64) - 1
 TIME_INF = (1 << 64) - 1
+U64 = (1 << 64) - 1
+PACK_MAX_CAND = 64        # candidates (class, variant) of the packed level; more => plain first-fit
+PACK_MAX_ITER = 64        # fill iterations per worker
+PACK_CHUNK_DIV = 8        # a pick takes at most max(1, quota / 8) tasks
 
 assignment_dtype = np.dtype([("task", "<u4"), ("worker", "<u2"), ("variant", "u1"), ("kind", "u1")])
 
@@ -46,71 +62,229 @@ def class_order(wl: Workload, free: np.ndarray, total: np.ndarray) -> List[int]:
     return [c for _, c in sorted(scores, key=lambda sc: -sc[0])]      # stable
 
 
+def variant_order(wl: Workload, free: np.ndarray) -> List[List[int]]:
+    """Per class: variants by ascending dominant share max_r amount_r / S_r (S_r = total free of r at tick
+    start): the variant that costs least of the scarcest thing it touches is tried first."""
+    W, R = free.shape
+    S = [0.0] * R
+    for w in range(W):
+        for r in range(R):
+            f = int(free[w, r])
+            S[r] += 1.0 if f == AMOUNT_MAX else f / 10000.0
+    out = []
+    for vs in wl.classes:
+        doms = []
+        for v, d in enumerate(vs):
+            dom = 0.0
+            for r in range(R):
+                a = int(d["amounts"].get(r, 0))
+                if a:
+                    x = float("inf") if S[r] < 1e-6 else (a / 10000.0) / S[r]
+                    dom = x if x > dom else dom
+            if d.get("all", ()):
+                dom = float("inf")
+            doms.append((dom, v))
+        out.append([v for _, v in sorted(doms, key=lambda dv: dv[0])])      # stable
+    return out
+
+
+def _sat_add(a: int, b: int) -> int:
+    return min(a + b, U64)
+
+
+def _sat_mul(a: int, b: int) -> int:
+    return min(a * b, U64)
+
+
+class _Tick:
+    def __init__(self, wl: Workload, free: np.ndarray, remaining_ms: np.ndarray) -> None:
+        self.wl = wl
+        self.W, self.R = free.shape
+        self.fr = [[int(x) for x in free[w]] for w in range(self.W)]
+        self.tot = [[int(x) for x in wl.worker_total[w]] for w in range(self.W)]
+        self.rem_ms = [int(x) for x in remaining_ms]
+        self.am = [[{r: int(a) for r, a in d["amounts"].items()} for d in vs] for vs in wl.classes]
+        self.alls = [[tuple(d.get("all", ())) for d in vs] for vs in wl.classes]
+        self.min_ms = [[int(round(d.get("min_time_s", 0.0) * 1000)) for d in vs] for vs in wl.classes]
+
+    def admissible(self, w: int, c: int, v: int) -> bool:
+        if self.wl.blocked is not None and self.wl.blocked[w, c, v]:
+            return False
+        rt = self.rem_ms[w]
+        return rt == TIME_INF or self.min_ms[c][v] <= rt
+
+    def fit(self, w: int, c: int, v: int, cap: int) -> int:
+        """How many tasks of (c, v) fit on worker w now, at most `cap`."""
+        if not self.admissible(w, c, v):
+            return 0
+        cnt = cap
+        fr, tot = self.fr[w], self.tot[w]
+        for r in range(self.R):
+            if r in self.alls[c][v]:
+                cnt = min(cnt, 1 if (tot[r] != 0 and fr[r] == tot[r]) else 0)
+            elif r in self.am[c][v] and fr[r] != AMOUNT_MAX:
+                cnt = min(cnt, fr[r] // self.am[c][v][r])
+        return cnt
+
+    def take(self, w: int, c: int, v: int, k: int) -> None:
+        fr = self.fr[w]
+        for r in range(self.R):
+            if r in self.alls[c][v]:
+                fr[r] = 0
+            elif r in self.am[c][v] and fr[r] != AMOUNT_MAX:
+                fr[r] -= k * self.am[c][v][r]
+
+    def give_back(self, w: int, c: int, v: int, k: int) -> None:
+        fr = self.fr[w]
+        for r, a in self.am[c][v].items():
+            if fr[r] != AMOUNT_MAX:
+                fr[r] += k * a
+
+
+def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[List[int]]) -> bool:
+    """Demand of the level (each class with its first variant of the tick's variant order) against the
+    aggregate free capacity, exact saturating u64 arithmetic."""
+    R, W = t.R, t.W
+    C = [0] * R
+    for r in range(R):
+        s = 0
+        for w in range(W):
+            s = U64 if t.fr[w][r] == AMOUNT_MAX else _sat_add(s, t.fr[w][r])
+            if s == U64:
+                break
+        C[r] = s
+    D = [0] * R
+    for c, n in groups:
+        for r, a in t.am[c][vorder[c][0]].items():
+            D[r] = _sat_add(D[r], _sat_mul(n, a))
+    return any(C[r] != U64 and D[r] > C[r] for r in range(R))
+
+
+def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int], List[int]]:
+    """Every worker fills itself (its free vector is consumed).  Returns taken[(group index, variant)][w]."""
+    W, R = t.W, t.R
+    cands = [(gi, c, v) for gi, (c, n) in enumerate(groups) for v in range(len(t.am[c]))]
+    # a. per-worker quotas
+    quota = [[0] * len(groups) for _ in range(W)]
+    for gi, (c, n) in enumerate(groups):
+        cn = [max(t.fit(w, c, v, n) for v in range(len(t.am[c]))) for w in range(W)]
+        T = sum(cn)
+        if T:
+            for w in range(W):
+                quota[w][gi] = -(-n * cn[w] // T)
+    # b. every worker fills itself
+    taken: Dict[Tuple[int, int], int] = {}       # (w, candidate index) -> count
+    for w in range(W):
+        tot = t.tot[w]
+        dvec, norm = [], []
+        for (gi, c, v) in cands:
+            d = [0.0] * R
+            for r, a in t.am[c][v].items():
+                if tot[r] != 0 and tot[r] != AMOUNT_MAX:
+                    d[r] = float(a) / float(tot[r])
+            s2 = 0.0
+            for r in range(R):
+                s2 = s2 + d[r] * d[r]
+            dvec.append(d)
+            norm.append(math.sqrt(s2))
+        for _ in range(PACK_MAX_ITER):
+            fr = t.fr[w]
+            u = [(float(fr[r]) / float(tot[r])) if (tot[r] != 0 and tot[r] != AMOUNT_MAX) else 0.0 for r in range(R)]
+            best, best_s = -1, 0.0
+            for ci, (gi, c, v) in enumerate(cands):
+                if quota[w][gi] <= 0 or not t.admissible(w, c, v):
+                    continue
+                if any(fr[r] != AMOUNT_MAX and a > fr[r] for r, a in t.am[c][v].items()):
+                    continue
+                dot = 0.0
+                for r in range(R):
+                    dot = dot + dvec[ci][r] * u[r]
+                s = dot / norm[ci] if norm[ci] > 0.0 else 0.0
+                if best < 0 or s > best_s:
+                    best, best_s = ci, s
+            if best < 0:
+                break
+            gi, c, v = cands[best]
+            q = quota[w][gi]
+            k = min(t.fit(w, c, v, q), max(1, q // PACK_CHUNK_DIV))
+            t.take(w, c, v, k)
+            quota[w][gi] -= k
+            taken[(w, best)] = taken.get((w, best), 0) + k
+    res: Dict[Tuple[int, int], List[int]] = {}
+    for ci, (gi, c, v) in enumerate(cands):
+        res[(gi, v)] = [taken.get((w, ci), 0) for w in range(W)]
+    return res
+
+
 def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Optional[np.ndarray] = None,
-               remaining_ms: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+               remaining_ms: Optional[np.ndarray] = None, pack: bool = True) -> Tuple[np.ndarray, np.ndarray]:
     """Returns (assignments in device emission order, free_after)."""
     W, R = free.shape
-    total = wl.worker_total
-    fr = [[int(x) for x in free[w]] for w in range(W)]
     prio = wl.task_user_priority.astype(np.int64)
     if levels is None:
         levels = np.unique(prio)[::-1]
     if remaining_ms is None:
         remaining_ms = wl.remaining_ms()
-    order = class_order(wl, free, total)
-    out = []
+    t = _Tick(wl, free, remaining_ms)
+    order = class_order(wl, free, wl.worker_total)
+    vorder = variant_order(wl, free)
+    out: List[Tuple[int, int, int, int]] = []
     ready_idx = np.nonzero(ready)[0]
     key_p = prio[ready_idx]
-    key_c = wl.task_class[ready_idx]
+    packed = not pack
     for lvl in levels.tolist():
         in_lvl = ready_idx[key_p == lvl]
         if in_lvl.size == 0:
             continue
         cls_lvl = wl.task_class[in_lvl]
-        for c in order:
-            tasks = in_lvl[cls_lvl == c]          # ascending handle
-            n = int(tasks.size)
-            if n == 0:
-                continue
-            remaining = n
+        tasks_of = {c: in_lvl[cls_lvl == c] for c in order}
+        groups = [(c, int(tasks_of[c].size)) for c in order if tasks_of[c].size]
+        taken: Dict[Tuple[int, int], List[int]] = {}
+        if not packed:
+            n_cand = sum(len(t.am[c]) for c, _ in groups)
+            has_all = any(t.alls[c][v] for c, _ in groups for v in range(len(t.am[c])))
+            if n_cand <= PACK_MAX_CAND and not has_all and _level_is_saturated(t, groups, vorder):
+                taken = _pack_level(t, groups)
+                packed = True
+        for gi, (c, n) in enumerate(groups):
+            tasks = tasks_of[c]
             pos = 0
-            for v, d in enumerate(wl.classes[c]):
+            # cap what the workers took for this class at its count, (variant, worker) order; hand the
+            # excess back
+            for v in range(len(t.am[c])):
+                tk = taken.get((gi, v))
+                if tk is None:
+                    continue
+                for w in range(W):
+                    k = tk[w]
+                    if not k:
+                        continue
+                    use = min(k, n - pos)
+                    if use < k:
+                        t.give_back(w, c, v, k - use)
+                    for tt in tasks[pos: pos + use].tolist():
+                        out.append((tt, w, v, 0))
+                    pos += use
+            remaining = n - pos
+            for v in vorder[c]:
                 if remaining == 0:
                     break
-                amounts = {r: int(a) for r, a in d["amounts"].items()}
-                alls = tuple(d.get("all", ()))
-                min_ms = int(round(d.get("min_time_s", 0.0) * 1000))
                 for w in range(W):
                     if remaining == 0:
                         break
-                    if wl.blocked is not None and wl.blocked[w, c, v]:
-                        continue
-                    rt = int(remaining_ms[w])
-                    if rt != TIME_INF and min_ms > rt:
-                        continue
-                    cnt = remaining
-                    for r in range(R):
-                        if r in alls:
-                            q = 1 if (int(total[w, r]) != 0 and fr[w][r] == int(total[w, r])) else 0
-                            cnt = min(cnt, q)
-                        elif r in amounts and fr[w][r] != AMOUNT_MAX:
-                            cnt = min(cnt, fr[w][r] // amounts[r])
+                    cnt = t.fit(w, c, v, remaining)
                     if cnt <= 0:
                         continue
-                    for r in range(R):
-                        if r in alls:
-                            fr[w][r] = 0
-                        elif r in amounts and fr[w][r] != AMOUNT_MAX:
-                            fr[w][r] -= cnt * amounts[r]
-                    for t in tasks[pos: pos + cnt].tolist():
-                        out.append((t, w, v, 0))
+                    t.take(w, c, v, cnt)
+                    for tt in tasks[pos: pos + cnt].tolist():
+                        out.append((tt, w, v, 0))
                     pos += cnt
                     remaining -= cnt
     a = np.array(out, dtype=assignment_dtype) if out else np.zeros(0, dtype=assignment_dtype)
-    return a, np.array(fr, dtype=np.uint64)
+    return a, np.array(t.fr, dtype=np.uint64)
 
 
-def model_drain(wl: Workload, max_ticks: int = 100000):
+def model_drain(wl: Workload, max_ticks: int = 100000, pack: bool = True):
     """Zero-duration drain with the model (independent tasks or DAG)."""
     n = wl.n_tasks
     if wl.deps is None:
@@ -127,7 +301,7 @@ def model_drain(wl: Workload, max_ticks: int = 100000):
     remaining = n
     per_tick = []
     while remaining > 0 and len(per_tick) < max_ticks:
-        a, _ = model_tick(wl, ready, wl.worker_free, levels)
+        a, _ = model_tick(wl, ready, wl.worker_free, levels, pack=pack)
         if a.size == 0:
             raise RuntimeError("model drain stalled")
         ready[a["task"]] = False

@@ -54,13 +54,18 @@ def test_no_cpu_fallback(lib):
 
 
 def test_product_does_not_import_oracle():
+    """The product path may not import, link or execute anything under oracle/ (or the test-only model)."""
     pkg = os.path.join(ROOT, "hyperqueue_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in src and "from oracle" not in src, f
-                assert "greedy_model" not in src, f
+            src = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".cu", ".h")) else ""
+            if f.endswith(".py"):
+                assert not re.search(r"^\s*(import|from)\s+(oracle|greedy_model|parity)\b", src, flags=re.M), f
+            if f.endswith((".cu", ".h")):
+                assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f
+    so = os.path.join(pkg, "libhqsched_b200.so")
+    out = __import__("subprocess").run(["ldd", so], capture_output=True, text=True).stdout
+    assert "hqjudge" not in out and "oracle" not in out
 
 
 def test_priority_mapping_matches_oracle():
