@@ -184,10 +184,8 @@ count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32
     __syncthreads();
     const u32 base = blockIdx.x * chunk;
     const u32 end = min(base + chunk, n_handles);
-    const u32 lane = threadIdx.x & 31;
     // chunk and base are multiples of 256 => 16-byte aligned uint4 loads; a ragged tail is scalar.
     const u32 vec_end = base + ((end - base) & ~3u);
-    // the loop is uniform across the CTA (the warp collectives below need all 32 lanes)
     for (u32 rowb = base; rowb < end; rowb += blockDim.x * 4) {
         const u32 i = rowb + threadIdx.x * 4;
         u32 k[4];
@@ -200,14 +198,9 @@ count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const bool ready = (k[j] & KEY_READY) != 0;
-            const u32 g = key_level(k[j]) * Q + key_class(k[j]);
-            // warp-aggregated shared-memory increment (few hot groups under a skewed class mix)
-            const u32 act = __ballot_sync(0xffffffffu, ready);
-            if (ready) {
-                const u32 peers = __match_any_sync(act, g);
-                if ((u32)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[g], (u32)__popc(peers));
-            }
+            // keys inside one warp are mostly distinct (levels x classes), so plain shared-memory atomics
+            // beat warp aggregation (match.any costs one round per distinct key)
+            if (k[j] & KEY_READY) atomicAdd(&s_hist[key_level(k[j]) * Q + key_class(k[j])], 1u);
         }
     }
     __syncthreads();
@@ -272,6 +265,8 @@ struct SolveArgs {
     u32 W, Q, L, R, G;
     u32 classes_bytes;       // Q * sizeof(ClassT<RT>)
     u32 smem_classes;        // 1: stage the class table in shared memory
+    u32 smem_glist_cap;      // group-list entries staged in shared memory
+    u32 smem_vorder;         // 1: stage vorder[] in shared memory
     u32 pack_enabled;
     // counts
     u32* total_local;        // [G] counts of this rank (zeroed here for the next tick)
@@ -500,9 +495,43 @@ __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u
     return o;
 }
 
+// First-fit hand-out with a single-taker fast path: when the first worker (in id order) that can take
+// anything can take ALL that is left — the usual case while capacity exceeds demand — one barrier settles
+// the step; otherwise fall back to the block-wide scan.
+__device__ __forceinline__ void hand_out(u64 cnt, u32 remaining, u64* s_x, u64* s_f, u32& parity, u32& take,
+                                         u32& exc_cnt, u32& seg_rank, u32& n_takers, u32& handed) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    u64* fb = s_f + 32 * (parity & 1);
+    const u32 has = __ballot_sync(0xffffffffu, cnt != 0);
+    const u32 first = has ? (u32)(__ffs(has) - 1) : 0u;
+    const u64 c0 = __shfl_sync(0xffffffffu, cnt, first);
+    if (lane == 0) fb[warp] = has ? ((1ull << 63) | c0) : 0ull;
+    __syncthreads();
+    const u64 e = lane < nwarps ? fb[lane] : 0ull;
+    const u32 anyw = __ballot_sync(0xffffffffu, (e >> 63) != 0);
+    if (!anyw) {                                   // nobody can take anything (uniform)
+        parity++;
+        take = exc_cnt = seg_rank = n_takers = handed = 0;
+        return;
+    }
+    const u32 wf = (u32)(__ffs(anyw) - 1);
+    const u64 c0w = __shfl_sync(0xffffffffu, e, wf) & ~(1ull << 63);
+    if (c0w >= remaining) {
+        parity++;
+        take = (warp == wf && lane == first && has) ? remaining : 0;
+        exc_cnt = 0; seg_rank = 0; n_takers = 1; handed = remaining;
+        return;
+    }
+    parity++;
+    ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+    take = o.take; exc_cnt = o.exc_cnt;
+    n_takers = (u32)__syncthreads_count(o.take != 0);
+    handed = (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
+}
+
 template <int RT>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
-    __shared__ u64 s_x[64];
+    __shared__ u64 s_x[64], s_f[64];
     __shared__ u32 s_a[40], s_b[40];
     __shared__ u32 s_nlist;
     const u32 tid = threadIdx.x;
@@ -519,6 +548,18 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         for (u32 i = tid; i < a.classes_bytes / 16; i += blockDim.x) dst[i] = src[i];
         classes = reinterpret_cast<const ClassT<RT>*>(smem_dyn);
     }
+    // group list and variant order: uniform data read on the sequential critical path => shared memory
+    unsigned char* sp = smem_dyn + (a.smem_classes ? ((a.classes_bytes + 15u) & ~15u) : 0u);
+    uint2* s_glist = reinterpret_cast<uint2*>(sp);
+    sp += (size_t)a.smem_glist_cap * sizeof(uint2);
+    const uint8_t* vorder = a.vorder;
+    if (a.smem_vorder) {
+        uint8_t* sv = sp;
+        for (u32 i = tid; i < a.Q * HQS_MAX_VARIANTS; i += blockDim.x) sv[i] = a.vorder[i];
+        vorder = sv;
+    }
+    const u32 gl_cap = a.smem_glist_cap;
+#define GL(e) ((e) < gl_cap ? s_glist[(e)] : a.glist[(e)])
 
     u64 fr[RT], tot[RT];
 #pragma unroll
@@ -546,7 +587,11 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         __syncthreads();
         u32 off = s_nlist;
         for (u32 w2 = 0; w2 < warp; ++w2) off += s_a[w2];
-        if (n) a.glist[off + __popc(bal & ((1u << lane) - 1))] = make_uint2(g, n);
+        if (n) {
+            const u32 slot = off + __popc(bal & ((1u << lane) - 1));
+            a.glist[slot] = make_uint2(g, n);
+            if (slot < gl_cap) s_glist[slot] = make_uint2(g, n);
+        }
         __syncthreads();
         if (tid == 0) {
             u32 t = 0;
@@ -566,9 +611,9 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     u32 li = 0;
     while (li < n_list) {
         // ---- one priority level: entries [li, lj)
-        const u32 lvl = a.glist[li].x / a.Q;
+        const u32 lvl = GL(li).x / a.Q;
         u32 lj = li + 1;
-        while (lj < n_list && a.glist[lj].x / a.Q == lvl) ++lj;
+        while (lj < n_list && GL(lj).x / a.Q == lvl) ++lj;
         const u32 ng = lj - li;
         bool level_packed = false;
 
@@ -577,7 +622,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             u32 n_cand = 0;
             bool has_all = false;
             for (u32 e = li; e < lj; ++e) {
-                const u32 c = a.glist[e].x % a.Q;
+                const u32 c = GL(e).x % a.Q;
                 n_cand += classes[c].n_variants;
                 for (u32 v = 0; v < classes[c].n_variants; ++v) has_all |= classes[c].v[v].all_mask != 0;
             }
@@ -612,12 +657,13 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (C == HQS_AMOUNT_MAX) continue;
                     u64 D = 0;
                     for (u32 e = li; e < lj && D != HQS_AMOUNT_MAX; ++e) {
-                        const u32 c = a.glist[e].x % a.Q;
-                        const VarT<RT>& dv = classes[c].v[a.vorder[c * HQS_MAX_VARIANTS]];
+                        const uint2 ge = GL(e);
+                        const u32 c = ge.x % a.Q;
+                        const VarT<RT>& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
                         u64 am = 0;
 #pragma unroll
                         for (int rr = 0; rr < RT; ++rr) if (rr == (int)r) am = dv.amount[rr];
-                        const unsigned __int128 p = (unsigned __int128)a.glist[e].y * am;
+                        const unsigned __int128 p = (unsigned __int128)ge.y * am;
                         const u64 pm = p > (unsigned __int128)HQS_AMOUNT_MAX ? HQS_AMOUNT_MAX : (u64)p;
                         const u64 s = D + pm;
                         D = s < D ? HQS_AMOUNT_MAX : s;
@@ -627,7 +673,8 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 if (saturated) {
                     // ---- a. quotas: share of each class proportional to how many fit on the worker alone
                     for (u32 e = li; e < lj; ++e) {
-                        const u32 c = a.glist[e].x % a.Q, n = a.glist[e].y;
+                        const uint2 ge = GL(e);
+                        const u32 c = ge.x % a.Q, n = ge.y;
                         const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
                         u64 cn = 0;
                         if (has_worker)
@@ -660,7 +707,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (tid == 0) {
                         u32 ci = 0;
                         for (u32 e = li; e < lj; ++e) {
-                            const u32 c = a.glist[e].x % a.Q;
+                            const u32 c = GL(e).x % a.Q;
                             for (u32 v = 0; v < classes[c].n_variants; ++v) a.pk.cand[ci++] = c | (v << 16) | ((e - li) << 24);
                         }
                         a.pk.meta[0] = ci;
@@ -695,7 +742,8 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         // ---- the groups of the level, in order: cap what pack took, then first-fit the rest
         u32 cand_base = 0;
         for (u32 e = li; e < lj; ++e) {
-            const u32 g = a.glist[e].x, n_all = a.glist[e].y;
+            const uint2 ge = GL(e);
+            const u32 g = ge.x, n_all = ge.y;
             const u32 c = g % a.Q;
             const u32 nv = classes[c].n_variants;
             u32 remaining = n_all;
@@ -728,31 +776,32 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 cand_base += nv;
             }
             for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
-                const u32 v = a.vorder[c * HQS_MAX_VARIANTS + vi];
+                const u32 v = vorder[c * HQS_MAX_VARIANTS + vi];
                 const VarT<RT>& dv = classes[c].v[v];
                 u64 cnt = 0;
                 if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, dv, remaining);
-                u32 seg_rank;
-                ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
-                if (o.take) {
+                u32 take, exc_cnt, seg_rank, n_takers, handed;
+                hand_out(cnt, remaining, s_x, s_f, parity, take, exc_cnt, seg_rank, n_takers, handed);
+                if (take) {
                     const u32 si = seg_base + seg_rank;
                     if (si < SEG_CAP) {
-                        a.seg_cum[si] = (n_all - remaining) + o.exc_cnt + o.take;
+                        a.seg_cum[si] = (n_all - remaining) + exc_cnt + take;
                         a.seg_wv[si] = tid | (v << 16);
                     }
-                    take_from<RT>(fr, dv, o.take);
+                    take_from<RT>(fr, dv, take);
                 }
-                const u32 n_takers = (u32)__syncthreads_count(o.take != 0);
-                remaining -= (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
+                remaining -= handed;
                 seg_base += n_takers;
                 if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
             }
             const u32 k = n_all - remaining;
             // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
-            const u32 bef = a.before ? a.before[g] : 0;
-            const u32 loc = a.total_local[g];
-            u32 k_loc = k > bef ? k - bef : 0;
-            k_loc = k_loc < loc ? k_loc : loc;
+            u32 k_loc = k;
+            if (a.before) {
+                const u32 bef = a.before[g], loc = a.total_local[g];
+                k_loc = k > bef ? k - bef : 0;
+                k_loc = k_loc < loc ? k_loc : loc;
+            }
             if (tid == 0) {
                 GroupOut go;
                 go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_base - seg_lo;
@@ -778,10 +827,11 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     }
     __syncthreads();
     for (u32 g = tid; g < a.G; g += blockDim.x) a.total_local[g] = 0;
+#undef GL
 }
 
-template <int RT>
-__global__ void __launch_bounds__(1024) solve_k(SolveArgs a) {
+template <int RT, int MAXT>
+__global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     if (blockIdx.x == 0) {
         solve_body<RT>(a, smem_dyn);
@@ -838,8 +888,20 @@ __global__ void __launch_bounds__(1024) solve_k(SolveArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr u32 EMIT_SEG_SMEM = 1024;
 
+// lanes of the warp holding the same group id, in constant time: one ballot per key bit (match.any
+// iterates once per DISTINCT key, and a warp of 32 tasks holds ~30 distinct (level, class) keys)
+__device__ __forceinline__ u32 same_key_lanes(u32 act, u32 g, u32 nbits) {
+    u32 peers = act;
+    for (u32 b = 0; b < nbits; ++b) {
+        const u32 bit = (g >> b) & 1u;
+        const u32 bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 __global__ void __launch_bounds__(1024)
-emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem, const u32* __restrict__ table,
+emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem, u32 nbits, const u32* __restrict__ table,
        const u32* __restrict__ before, const GroupOut* __restrict__ gout, const u32* __restrict__ seg_cum,
        const u32* __restrict__ seg_wv, const TickHeaderOut* __restrict__ hdr, hqs_assignment* __restrict__ out,
        u32 out_cap) {
@@ -872,10 +934,8 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
         const bool ready = (k & KEY_READY) != 0;
         const u32 g = key_level(k) * Q + key_class(k);
         const u32 act = __ballot_sync(0xffffffffu, ready);
-        if (ready) {
-            const u32 peers = __match_any_sync(act, g);
-            if ((u32)(__ffs(peers) - 1) == lane) mycnt[g] += __popc(peers);
-        }
+        const u32 peers = same_key_lanes(act, g, nbits);
+        if (ready && (u32)(__ffs(peers) - 1) == lane) mycnt[g] += __popc(peers);
         if (i - lane + 32 >= wend) break;   // uniform: whole row past the end
     }
     __syncthreads();
@@ -897,8 +957,8 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
         const bool ready = (k & KEY_READY) != 0;
         const u32 g = key_level(k) * Q + key_class(k);
         const u32 act = __ballot_sync(0xffffffffu, ready);
+        const u32 peers = same_key_lanes(act, g, nbits);
         if (ready) {
-            const u32 peers = __match_any_sync(act, g);
             const u32 leader = __ffs(peers) - 1;
             u32 r0 = 0;
             if (leader == lane) {
@@ -1247,12 +1307,14 @@ void tick_orders(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total
     for (u32 c = 0; c < Q; ++c) order[c] = sc[c].second;
 }
 
-struct TickGeom { u32 G, L, P, chunk, emit_warps, g_smem; size_t emit_smem; };
+struct TickGeom { u32 G, L, P, chunk, emit_warps, g_smem, nbits; size_t emit_smem; };
 
 TickGeom tick_geom(const hqs_ctx* ctx) {
     TickGeom t;
     t.L = std::max<u32>((u32)ctx->dev_levels.size(), 1);
     t.G = t.L * std::max<u32>(ctx->Q, 1);
+    t.nbits = 1;
+    while ((1u << t.nbits) < t.G) t.nbits++;
     // emit_k shared memory: warps * G counters (+ G solver records + the segment cache); as many warps per
     // CTA as the budget allows, two CTAs per SM
     const size_t seg_cache = 2 * EMIT_SEG_SMEM * sizeof(u32);
@@ -1332,7 +1394,7 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.classes = ctx->d_classes;
     a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
     a.classes_bytes = ctx->Q * ctx->class_bytes;
-    a.smem_classes = a.classes_bytes <= 64 * 1024 ? 1 : 0;
+    a.smem_classes = a.classes_bytes <= 48 * 1024 ? 1 : 0;
     a.total_local = ctx->d_total;
     a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
     a.before = d_before;
@@ -1353,15 +1415,21 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     u32 grid = std::max<u32>(1 + a.scan_ctas, std::min<u32>(ctx->sm_count, 1 + (W + 1) / 2));
     grid = std::min<u32>(grid, ctx->sm_count);
     a.pack_enabled = (ctx->pack && grid >= 2) ? 1 : 0;
-    const size_t solve_smem = a.smem_classes ? a.classes_bytes : 0;
+    size_t solve_smem = a.smem_classes ? ((a.classes_bytes + 15u) & ~15u) : 0;
+    a.smem_glist_cap = std::min<u32>(t.G, 2048);
+    solve_smem += (size_t)a.smem_glist_cap * sizeof(uint2);
+    a.smem_vorder = ctx->Q <= 1024 ? 1 : 0;
+    if (a.smem_vorder) solve_smem += (size_t)ctx->Q * HQS_MAX_VARIANTS;
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
     void* kargs[] = {&a};
-    const void* fn = ctx->RT == 4 ? (const void*)solve_k<4> : ctx->RT == 8 ? (const void*)solve_k<8> : (const void*)solve_k<16>;
+    const void* fn;
+    if (threads <= 256) fn = ctx->RT == 4 ? (const void*)solve_k<4, 256> : ctx->RT == 8 ? (const void*)solve_k<8, 256> : (const void*)solve_k<16, 256>;
+    else fn = ctx->RT == 4 ? (const void*)solve_k<4, 1024> : ctx->RT == 8 ? (const void*)solve_k<8, 1024> : (const void*)solve_k<16, 1024>;
     CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
     ctx->stats.kernel_launches++;
     if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     emit_k<<<t.P, 32 * t.emit_warps, t.emit_smem, ctx->stream>>>(
-        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, t.g_smem, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
+        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, t.g_smem, t.nbits, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
         ctx->d_seg_wv, ctx->d_hdr, ctx->d_out, out_cap);
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
@@ -1410,9 +1478,12 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete ctx;
