@@ -304,6 +304,29 @@ def run_cuda(args) -> None:
     else:
         roofline = None
 
+    # ---- mode M2: zero-duration drain of the same task set with REAL capacities
+    #      (256 workers x {128 cpus, 8 gpus, 512 GiB, 2048 GiB}); every tick goes through the public call
+    drain = None
+    if rank == 0 and world == 1 and not args.no_drain:
+        wl2 = make_workload(N_TASKS, seed=0, free_scale=1)
+        s2 = P.gpu_scheduler(wl2, device=local_rank)
+        s2.run_scheduling(); s2.rearm(); s2.free = wl2.worker_free.copy()          # allocate, then re-arm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        left, ticks = N_TASKS, 0
+        while left > 0 and ticks < 5000:
+            m = s2.run_scheduling()
+            if m.n_assigned() == 0:
+                break
+            left -= m.n_assigned()
+            ticks += 1
+            s2.tasks_finished(m.assignments["task"])
+        dt = time.perf_counter() - t0
+        drain = {"value": (N_TASKS - left) / dt, "unit": "assignments/s", "ticks": ticks, "seconds": dt,
+                 "ms_per_tick": 1000.0 * dt / max(ticks, 1), "assigned": N_TASKS - left,
+                 "note": "M2: hqs_tick per tick incl. worker upload, D2H of assignments and host-side resource return"}
+        s2.close()
+
     # ---- e2e: host buffers through the public C ABI -----------------------------------------------
     e2e = None
     if rank == 0:
@@ -350,7 +373,7 @@ def run_cuda(args) -> None:
                        "12 MB task table (K+W tables, 21 x 12 MB > 126 MB L2): inputs larger than L2",
                        "host_wall_ms_per_step": 1000.0 * t_host / K},
             "gpu_launches": launches_timed, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "drain_m2": drain,
         }))
     for s in scheds:
         s.close()
@@ -366,6 +389,7 @@ def main() -> None:
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--ref-sample", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-drain", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -67,6 +68,7 @@ struct TickHeaderOut {
     u32 n_groups;
     u32 n_segments;
     u32 error;       // 1 = segment overflow, 2 = solver grid synchronisation timed out
+    unsigned long long dbg[8];   // clock64 phase stamps of CTA 0 (debug)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -529,9 +531,10 @@ __device__ __forceinline__ void hand_out(u64 cnt, u32 remaining, u64* s_x, u64* 
     handed = (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
 }
 
-template <int RT>
+template <int RT, bool SMALL>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     __shared__ u64 s_x[64], s_f[64];
+    __shared__ u64 s_red[2 * 32 * (2 * RT + 1)];
     __shared__ u32 s_a[40], s_b[40];
     __shared__ u32 s_nlist;
     const u32 tid = threadIdx.x;
@@ -540,27 +543,32 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     const bool has_worker = tid < a.W;
     u32 parity = 0;
 
-    // ---- class table: shared memory when it fits, else global (uniform loads)
-    const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
-    if (a.smem_classes) {
+    // ---- class table and variant order: in shared memory when they fit (SMALL: the pointers are then
+    //      provably shared, so the sequential critical path uses LDS, not generic loads), else global
+    const ClassT<RT>* classes;
+    const uint8_t* vorder;
+    unsigned char* sp = smem_dyn;
+    if constexpr (SMALL) {
         const uint4* src = reinterpret_cast<const uint4*>(a.classes);
         uint4* dst = reinterpret_cast<uint4*>(smem_dyn);
         for (u32 i = tid; i < a.classes_bytes / 16; i += blockDim.x) dst[i] = src[i];
         classes = reinterpret_cast<const ClassT<RT>*>(smem_dyn);
-    }
-    // group list and variant order: uniform data read on the sequential critical path => shared memory
-    unsigned char* sp = smem_dyn + (a.smem_classes ? ((a.classes_bytes + 15u) & ~15u) : 0u);
-    uint2* s_glist = reinterpret_cast<uint2*>(sp);
-    sp += (size_t)a.smem_glist_cap * sizeof(uint2);
-    const uint8_t* vorder = a.vorder;
-    if (a.smem_vorder) {
+        sp += (a.classes_bytes + 15u) & ~15u;
         uint8_t* sv = sp;
         for (u32 i = tid; i < a.Q * HQS_MAX_VARIANTS; i += blockDim.x) sv[i] = a.vorder[i];
         vorder = sv;
+        sp += (a.Q * HQS_MAX_VARIANTS + 15u) & ~15u;
+    } else {
+        classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
+        vorder = a.vorder;
     }
+    uint2* s_glist = reinterpret_cast<uint2*>(sp);
+    uint8_t* s_alive = sp + (size_t)a.smem_glist_cap * sizeof(uint2);   // [gl_cap] group still placeable
     const u32 gl_cap = a.smem_glist_cap;
 #define GL(e) ((e) < gl_cap ? s_glist[(e)] : a.glist[(e)])
 
+    const long long t_start = clock64();
+    long long t_sat = 0, t_groups = 0;
     u64 fr[RT], tot[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -601,6 +609,11 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         __syncthreads();
     }
     const u32 n_list = s_nlist;
+    for (u32 e = tid; e < gl_cap; e += blockDim.x) s_alive[e] = 1;
+    // groups without ready tasks keep k = 0 (emit_k's chunk filter reads k of every group)
+    for (u32 g = tid; g < a.G; g += blockDim.x) a.gout[g].k = 0;
+    __syncthreads();
+    const long long t_compact = clock64();
 
     u32 seg_base = 0;    // uniform across the CTA
     u32 out_base = 0;    // uniform: local output offset
@@ -616,59 +629,63 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         while (lj < n_list && GL(lj).x / a.Q == lvl) ++lj;
         const u32 ng = lj - li;
         bool level_packed = false;
+        const long long t_l0 = clock64();
 
         if (!packed && ng <= PACK_MAX_CAND) {
-            // ---- is this level saturated?  demand (first variant of the tick's order) vs free, exact u64
-            u32 n_cand = 0;
-            bool has_all = false;
-            for (u32 e = li; e < lj; ++e) {
-                const u32 c = GL(e).x % a.Q;
-                n_cand += classes[c].n_variants;
-                for (u32 v = 0; v < classes[c].n_variants; ++v) has_all |= classes[c].v[v].all_mask != 0;
+            // ---- is this level saturated?  demand (first variant of the tick's order) vs free, exact
+            //      saturating u64.  Thread t < ng owns group li + t; one exchange reduces, per resource, the
+            //      free capacity over workers and the demand over groups, plus the candidate count.
+            constexpr int NV = 2 * RT + 1;
+            u64 val[NV];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) { val[r] = has_worker ? fr[r] : 0; val[RT + r] = 0; }
+            val[2 * RT] = 0;
+            if (tid < ng) {
+                const uint2 ge = GL(li + tid);
+                const u32 c = ge.x % a.Q;
+                const u32 nvv = classes[c].n_variants;
+                u64 flag = 0;
+                for (u32 v = 0; v < nvv; ++v) flag |= classes[c].v[v].all_mask ? (1ull << 32) : 0ull;
+                val[2 * RT] = nvv | flag;                                  // low: candidates, bit 32+: has `All`
+                const VarT<RT>& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const u64 hi = __umul64hi(dv.amount[r], (u64)ge.y);
+                    val[RT + r] = hi ? HQS_AMOUNT_MAX : dv.amount[r] * (u64)ge.y;
+                }
             }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const u64 y = __shfl_xor_sync(0xffffffffu, val[i], d);
+                    const u64 sum = val[i] + y;
+                    val[i] = sum < y ? HQS_AMOUNT_MAX : sum;              // saturating (MAX absorbs)
+                }
+            }
+            u64* red = s_red + (size_t)(parity & 1) * 32 * NV;
+            parity++;
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) red[warp * NV + i] = val[i];
+            }
+            __syncthreads();
+            u64 tot_v = 0;                                                 // lane i < NV sums column i over warps
+            if (lane < NV)
+                for (u32 w2 = 0; w2 < nwarps; ++w2) {
+                    const u64 y = red[w2 * NV + lane];
+                    const u64 sum = tot_v + y;
+                    tot_v = sum < y ? HQS_AMOUNT_MAX : sum;
+                }
+            const u64 meta = __shfl_sync(0xffffffffu, tot_v, 2 * RT);
+            const u32 n_cand = (u32)(meta & 0xFFFFFFFFu);
+            const bool has_all = (meta >> 32) != 0;
             if (n_cand <= PACK_MAX_CAND && !has_all) {
                 bool saturated = false;
                 for (u32 r = 0; r < a.R; ++r) {
-                    // C_r = saturating sum of free over workers (MAX => unbounded)
-                    u64 x = 0;
-#pragma unroll
-                    for (int rr = 0; rr < RT; ++rr) if (rr == (int)r) x = fr[rr];
-                    if (!has_worker) x = 0;
-                    bool inf = has_worker && x == HQS_AMOUNT_MAX;
-                    // warp then block reduction with saturation
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) {
-                        const u64 y = __shfl_xor_sync(0xffffffffu, x, d);
-                        const u64 s = x + y;
-                        x = s < x ? HQS_AMOUNT_MAX : s;
-                    }
-                    inf = __any_sync(0xffffffffu, inf);
-                    u64* buf = s_x + 32 * (parity & 1);
-                    parity++;
-                    if (lane == 0) buf[warp] = inf ? HQS_AMOUNT_MAX : x;
-                    __syncthreads();
-                    u64 C = 0;
-                    for (u32 w2 = 0; w2 < nwarps; ++w2) {
-                        const u64 y = buf[w2];
-                        const u64 s = C + y;
-                        C = (y == HQS_AMOUNT_MAX || s < C) ? HQS_AMOUNT_MAX : s;
-                        if (C == HQS_AMOUNT_MAX) break;
-                    }
-                    if (C == HQS_AMOUNT_MAX) continue;
-                    u64 D = 0;
-                    for (u32 e = li; e < lj && D != HQS_AMOUNT_MAX; ++e) {
-                        const uint2 ge = GL(e);
-                        const u32 c = ge.x % a.Q;
-                        const VarT<RT>& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
-                        u64 am = 0;
-#pragma unroll
-                        for (int rr = 0; rr < RT; ++rr) if (rr == (int)r) am = dv.amount[rr];
-                        const unsigned __int128 p = (unsigned __int128)ge.y * am;
-                        const u64 pm = p > (unsigned __int128)HQS_AMOUNT_MAX ? HQS_AMOUNT_MAX : (u64)p;
-                        const u64 s = D + pm;
-                        D = s < D ? HQS_AMOUNT_MAX : s;
-                    }
-                    if (D > C) saturated = true;
+                    const u64 C = __shfl_sync(0xffffffffu, tot_v, r);
+                    const u64 D = __shfl_sync(0xffffffffu, tot_v, RT + r);
+                    if (C != HQS_AMOUNT_MAX && D > C) saturated = true;
                 }
                 if (saturated) {
                     // ---- a. quotas: share of each class proportional to how many fit on the worker alone
@@ -739,9 +756,16 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             }
         }
 
+        const long long t_l1 = clock64();
+        t_sat += t_l1 - t_l0;
         // ---- the groups of the level, in order: cap what pack took, then first-fit the rest
         u32 cand_base = 0;
+        bool level_unsatisfied = false;
         for (u32 e = li; e < lj; ++e) {
+            if (e < gl_cap && !s_alive[e]) {                  // no worker can take a single task of it (uniform)
+                if (level_packed) cand_base += classes[GL(e).x % a.Q].n_variants;
+                continue;
+            }
             const uint2 ge = GL(e);
             const u32 g = ge.x, n_all = ge.y;
             const u32 c = g % a.Q;
@@ -778,10 +802,50 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
                 const u32 v = vorder[c * HQS_MAX_VARIANTS + vi];
                 const VarT<RT>& dv = classes[c].v[v];
-                u64 cnt = 0;
-                if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, dv, remaining);
-                u32 take, exc_cnt, seg_rank, n_takers, handed;
-                hand_out(cnt, remaining, s_x, s_f, parity, take, exc_cnt, seg_rank, n_takers, handed);
+                // can1: at least one task fits; canAll: all that is left fits (no division: compares and
+                // one multiply per resource).  The exact count is only needed when the block-wide scan runs.
+                bool can1 = false, can_all = false;
+                if (has_worker && admissible(dv, v, blk, rem_time)) {
+                    can1 = can_all = true;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        if (!((dv.used_mask >> r) & 1)) continue;
+                        if ((dv.all_mask >> r) & 1) {
+                            const bool ok = tot[r] != 0 && fr[r] == tot[r];
+                            can1 &= ok; can_all &= ok && remaining <= 1;
+                        } else if (fr[r] != HQS_AMOUNT_MAX) {
+                            can1 &= dv.amount[r] <= fr[r];
+                            can_all &= __umul64hi(dv.amount[r], (u64)remaining) == 0 && dv.amount[r] * (u64)remaining <= fr[r];
+                        }
+                    }
+                    can_all &= can1;
+                }
+                u32 take = 0, exc_cnt = 0, seg_rank = 0, n_takers = 0, handed = 0;
+                {
+                    u64* fb = s_f + 32 * (parity & 1);
+                    parity++;
+                    const u32 has = __ballot_sync(0xffffffffu, can1);
+                    const u32 first = has ? (u32)(__ffs(has) - 1) : 0u;
+                    const u32 fall = __shfl_sync(0xffffffffu, can_all ? 1u : 0u, first);
+                    if (lane == 0) fb[warp] = has ? (2ull | fall) : 0ull;
+                    __syncthreads();
+                    const u64 ee = lane < nwarps ? fb[lane] : 0ull;
+                    const u32 anyw = __ballot_sync(0xffffffffu, ee != 0);
+                    if (anyw) {
+                        const u32 wf = (u32)(__ffs(anyw) - 1);
+                        const u64 ef = __shfl_sync(0xffffffffu, ee, wf);
+                        if (ef & 1ull) {                       // the first worker that can take anything takes it all
+                            take = (warp == wf && lane == first && can1) ? remaining : 0;
+                            n_takers = 1; handed = remaining;
+                        } else {
+                            const u64 cnt = can1 ? fit_count<RT>(fr, tot, dv, remaining) : 0;
+                            ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+                            take = o.take; exc_cnt = o.exc_cnt;
+                            n_takers = (u32)__syncthreads_count(o.take != 0);
+                            handed = (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
+                        }
+                    }
+                }
                 if (take) {
                     const u32 si = seg_base + seg_rank;
                     if (si < SEG_CAP) {
@@ -795,6 +859,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
             }
             const u32 k = n_all - remaining;
+            level_unsatisfied |= remaining != 0;
             // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
             u32 k_loc = k;
             if (a.before) {
@@ -809,8 +874,39 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             }
             out_base += k_loc;
         }
+        // ---- the level left tasks behind: the pool is filling up.  Free amounts only shrink from here on
+        //      (pack's hand-backs are over), so a later group that no worker can take one task of NOW can be
+        //      dropped for the rest of the tick: test all of them at once, one thread per worker.
+        if (level_unsatisfied && lj < n_list && n_list <= gl_cap) {
+            for (u32 e = lj; e < n_list; ++e) {
+                if (!s_alive[e]) continue;                                     // uniform
+                const u32 c = s_glist[e].x % a.Q;
+                const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
+                bool can = false;
+                if (has_worker)
+                    for (u32 v = 0; v < classes[c].n_variants && !can; ++v) {
+                        const VarT<RT>& dv = classes[c].v[v];
+                        if (!admissible(dv, v, blk, rem_time)) continue;
+                        bool ok = true;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            if (!((dv.used_mask >> r) & 1)) continue;
+                            if ((dv.all_mask >> r) & 1) ok &= tot[r] != 0 && fr[r] == tot[r];
+                            else if (fr[r] != HQS_AMOUNT_MAX) ok &= dv.amount[r] <= fr[r];
+                        }
+                        can = ok;
+                    }
+                const u32 anyc = __ballot_sync(0xffffffffu, can);
+                if (lane == 0 && anyc) s_alive[e] = 2;                          // 2 = confirmed this round
+            }
+            __syncthreads();
+            for (u32 e = lj + tid; e < n_list; e += blockDim.x) s_alive[e] = s_alive[e] == 2 ? 1 : 0;
+            __syncthreads();
+        }
+        t_groups += clock64() - t_l1;
         li = lj;
     }
+    const long long t_loop = clock64();
 
     // ---- epilogue: let the other CTAs go, header, free vectors after the tick, reset the counters
     if (tid == 0 && !signalled) st_release(&a.sync->phase, PHASE_EXIT);
@@ -824,17 +920,19 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         a.hdr->n_groups = n_list;
         a.hdr->n_segments = seg_base;
         a.hdr->error = sync_timeout ? 2u : (seg_overflow ? 1u : 0u);
+        a.hdr->dbg[0] = t_compact - t_start; a.hdr->dbg[1] = t_sat; a.hdr->dbg[2] = t_groups;
+        a.hdr->dbg[3] = t_loop - t_start; a.hdr->dbg[4] = n_list;
     }
     __syncthreads();
     for (u32 g = tid; g < a.G; g += blockDim.x) a.total_local[g] = 0;
 #undef GL
 }
 
-template <int RT, int MAXT>
+template <int RT, int MAXT, bool SMALL>
 __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     if (blockIdx.x == 0) {
-        solve_body<RT>(a, smem_dyn);
+        solve_body<RT, SMALL>(a, smem_dyn);
         return;
     }
     // ---- exclusive scan over chunks: one warp per group column, 32 chunk rows per step
@@ -913,6 +1011,18 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
     u32* s_segw = s_segc + EMIT_SEG_SMEM;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 i = threadIdx.x; i < nwarps * G; i += blockDim.x) s_cnt[i] = 0;
+    // A chunk holds an assigned task only if, for some group, fewer than k[g] tasks of the group precede
+    // the chunk (the assigned ones are the first k[g] in handle order): in a drain tick only the first
+    // chunks qualify, the rest leave after reading one table row.
+    {
+        const u32* row0 = table + (size_t)blockIdx.x * G;
+        bool mine = false;
+        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+            const u32 bef = before ? __ldg(before + g) : 0u;
+            mine |= row0[g] + bef < gout[g].k;
+        }
+        if (!__syncthreads_or(mine)) return;
+    }
     const u32 n_seg = hdr->n_segments;
     const bool seg_smem = n_seg <= EMIT_SEG_SMEM;
     if (g_smem)
@@ -1067,6 +1177,7 @@ struct hqs_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     hqs_stats stats{};
+    unsigned long long dbg[8] = {0};
 };
 
 namespace {
@@ -1394,7 +1505,6 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.classes = ctx->d_classes;
     a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
     a.classes_bytes = ctx->Q * ctx->class_bytes;
-    a.smem_classes = a.classes_bytes <= 48 * 1024 ? 1 : 0;
     a.total_local = ctx->d_total;
     a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
     a.before = d_before;
@@ -1415,17 +1525,24 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     u32 grid = std::max<u32>(1 + a.scan_ctas, std::min<u32>(ctx->sm_count, 1 + (W + 1) / 2));
     grid = std::min<u32>(grid, ctx->sm_count);
     a.pack_enabled = (ctx->pack && grid >= 2) ? 1 : 0;
-    size_t solve_smem = a.smem_classes ? ((a.classes_bytes + 15u) & ~15u) : 0;
+    // SMALL variant: class table + variant order staged in shared memory
+    a.smem_classes = ((size_t)a.classes_bytes + (size_t)ctx->Q * HQS_MAX_VARIANTS <= 48 * 1024) ? 1 : 0;
+    a.smem_vorder = a.smem_classes;
+    size_t solve_smem = 0;
+    if (a.smem_classes) solve_smem += ((a.classes_bytes + 15u) & ~15u) + ((ctx->Q * HQS_MAX_VARIANTS + 15u) & ~15u);
     a.smem_glist_cap = std::min<u32>(t.G, 2048);
-    solve_smem += (size_t)a.smem_glist_cap * sizeof(uint2);
-    a.smem_vorder = ctx->Q <= 1024 ? 1 : 0;
-    if (a.smem_vorder) solve_smem += (size_t)ctx->Q * HQS_MAX_VARIANTS;
+    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + 1) + 16;
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
     void* kargs[] = {&a};
+    const bool small = a.smem_classes != 0;
     const void* fn;
-    if (threads <= 256) fn = ctx->RT == 4 ? (const void*)solve_k<4, 256> : ctx->RT == 8 ? (const void*)solve_k<8, 256> : (const void*)solve_k<16, 256>;
-    else fn = ctx->RT == 4 ? (const void*)solve_k<4, 1024> : ctx->RT == 8 ? (const void*)solve_k<8, 1024> : (const void*)solve_k<16, 1024>;
-    CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
+#define HQS_PICK(MT, SM) (ctx->RT == 4 ? (const void*)solve_k<4, MT, SM> : ctx->RT == 8 ? (const void*)solve_k<8, MT, SM> : (const void*)solve_k<16, MT, SM>)
+    if (threads <= 256) fn = small ? HQS_PICK(256, true) : HQS_PICK(256, false);
+    else fn = small ? HQS_PICK(1024, true) : HQS_PICK(1024, false);
+#undef HQS_PICK
+    static const bool no_coop = getenv("HQS_DEBUG_NO_COOP") != nullptr;   // profiling aid: ncu skips cooperative launches
+    if (no_coop) CU(cudaLaunchKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
+    else CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
     ctx->stats.kernel_launches++;
     if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     emit_k<<<t.P, 32 * t.emit_warps, t.emit_smem, ctx->stream>>>(
@@ -1478,12 +1595,18 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete ctx;
@@ -1778,6 +1901,7 @@ int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t
     ctx->stats.n_levels = ctx->last_L;
     ctx->stats.n_assigned = hdr.n_assigned;
     ctx->stats.n_segments = hdr.n_segments;
+    memcpy(ctx->dbg, hdr.dbg, sizeof ctx->dbg);
     if (hdr.error == 2) return fail(ctx, HQS_E_CUDA, "solver grid synchronisation timed out");
     if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
     if (hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
@@ -1883,6 +2007,12 @@ int hqs_sync(hqs_ctx* ctx) {
     if (!ctx) return HQS_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    return HQS_OK;
+}
+
+int hqs_debug_read(hqs_ctx* ctx, uint64_t out[8]) {
+    if (!ctx || !out) return HQS_E_INVALID;
+    for (int i = 0; i < 8; ++i) out[i] = ctx->dbg[i];
     return HQS_OK;
 }
 

@@ -178,6 +178,9 @@ int hqs_set_stream(hqs_ctx* ctx, void* cuda_stream);
  * out_ms[0..2] = count_k, solve_k, emit_k of the last fetched/synchronised tick, out_ms[3] = their sum. */
 int hqs_set_profile(hqs_ctx* ctx, int on);
 int hqs_get_kernel_ms(hqs_ctx* ctx, float out_ms[4]);
+/* Debug: clock64 phase stamps of the solver CTA of the last fetched tick (compaction, saturation tests,
+ * group loop, total, non-empty groups). */
+int hqs_debug_read(hqs_ctx* ctx, uint64_t out[8]);
 int hqs_sync(hqs_ctx* ctx);
 int hqs_get_stats(hqs_ctx* ctx, hqs_stats* out);
 
