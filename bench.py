@@ -177,6 +177,8 @@ def run_cuda(args) -> None:
         s._sync_classes()
         s._check(s._lib.hqs_set_stream(s._ctx, C.c_void_p(stream.cuda_stream)))
         # distinct device tables; rotate the class/priority arrays so the tables differ
+        lv = np.ascontiguousarray(np.unique(prio))
+        s._check(s._lib.hqs_levels_add(s._ctx, lv.size, L.ptr(lv)))      # same level numbering on every rank
         s.add_ready_tasks(handles, np.roll(wl.task_class, i * 7919), np.roll(prio, i * 7919))
         scheds.append(s)
     torch.cuda.synchronize()

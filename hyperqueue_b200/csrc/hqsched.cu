@@ -497,40 +497,6 @@ __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u
     return o;
 }
 
-// First-fit hand-out with a single-taker fast path: when the first worker (in id order) that can take
-// anything can take ALL that is left — the usual case while capacity exceeds demand — one barrier settles
-// the step; otherwise fall back to the block-wide scan.
-__device__ __forceinline__ void hand_out(u64 cnt, u32 remaining, u64* s_x, u64* s_f, u32& parity, u32& take,
-                                         u32& exc_cnt, u32& seg_rank, u32& n_takers, u32& handed) {
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    u64* fb = s_f + 32 * (parity & 1);
-    const u32 has = __ballot_sync(0xffffffffu, cnt != 0);
-    const u32 first = has ? (u32)(__ffs(has) - 1) : 0u;
-    const u64 c0 = __shfl_sync(0xffffffffu, cnt, first);
-    if (lane == 0) fb[warp] = has ? ((1ull << 63) | c0) : 0ull;
-    __syncthreads();
-    const u64 e = lane < nwarps ? fb[lane] : 0ull;
-    const u32 anyw = __ballot_sync(0xffffffffu, (e >> 63) != 0);
-    if (!anyw) {                                   // nobody can take anything (uniform)
-        parity++;
-        take = exc_cnt = seg_rank = n_takers = handed = 0;
-        return;
-    }
-    const u32 wf = (u32)(__ffs(anyw) - 1);
-    const u64 c0w = __shfl_sync(0xffffffffu, e, wf) & ~(1ull << 63);
-    if (c0w >= remaining) {
-        parity++;
-        take = (warp == wf && lane == first && has) ? remaining : 0;
-        exc_cnt = 0; seg_rank = 0; n_takers = 1; handed = remaining;
-        return;
-    }
-    parity++;
-    ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
-    take = o.take; exc_cnt = o.exc_cnt;
-    n_takers = (u32)__syncthreads_count(o.take != 0);
-    handed = (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
-}
-
 template <int RT, bool SMALL>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     __shared__ u64 s_x[64], s_f[64];
@@ -1748,6 +1714,19 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
         if ((rc = relevel_all(ctx))) return rc;
     }
     return HQS_OK;
+}
+
+int hqs_levels_add(hqs_ctx* ctx, uint32_t n, const uint64_t* priority) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n == 0) return HQS_OK;
+    if (!priority) return fail(ctx, HQS_E_INVALID, "null priority array");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<u64> fresh;
+    distinct_priorities(priority, n, fresh);
+    if (!merge_levels(ctx, fresh)) return HQS_OK;
+    int rc = upload_levels(ctx);
+    if (rc) return rc;
+    return relevel_all(ctx);
 }
 
 int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task) {

@@ -1,0 +1,92 @@
+"""Multi-GPU sharding of the ready set: one process per GPU, the task table is
+block-sharded by handle, worker state is replicated.
+
+Per tick:
+  1. every rank histograms ITS ready tasks per (priority level, class) group     hqs_shard_count
+  2. all-gather of the count vectors (NCCL over NVLink; 4 B x groups per rank — the only data-path
+     collective), from which every rank derives   counts_all = sum over ranks
+                                                   ranks_before = sum over lower ranks   (shard_exchange)
+  3. every rank runs the SAME deterministic solve on counts_all (replicated worker state => identical
+     count segments everywhere) and emits only its own tasks: a task's global rank inside its group is
+     ranks_before[g] + its local rank                                           hqs_shard_solve_emit
+  4. the assignment lists are gathered where they are needed (host, or all-gather of (task, worker) pairs).
+No task data moves between GPUs.  The exchange logic is device-agnostic torch code so that it is covered
+by world_size-2 gloo tests on CPU (tests/test_sharded_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def shard_exchange(counts_local: torch.Tensor, rank: int, world: int,
+                   group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """counts_local: int32 [G] on any device.  Returns (counts_all, ranks_before), int32 [G]."""
+    if world == 1:
+        return counts_local.clone(), torch.zeros_like(counts_local)
+    gathered = torch.empty(world * counts_local.numel(), dtype=counts_local.dtype, device=counts_local.device)
+    dist.all_gather_into_tensor(gathered, counts_local.contiguous(), group=group)
+    g2 = gathered.view(world, -1).to(torch.int64)
+    counts_all = g2.sum(0).to(torch.int32)
+    before = g2[:rank].sum(0).to(torch.int32) if rank else torch.zeros_like(counts_local)
+    return counts_all, before
+
+
+def block_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous handle range [lo, hi) of a rank; ranks are ordered by handle so that lower ranks hold the
+    lower (earlier TaskId) handles — the global rank of a task inside its group needs exactly that."""
+    per = (n_total + world - 1) // world
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
+
+
+class ShardedScheduler:
+    """Wraps one GpuScheduler per rank.  Handles given to / returned from this class are GLOBAL."""
+
+    def __init__(self, sched, rank: int, world: int, n_total: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None) -> None:
+        self.s = sched
+        self.rank, self.world, self.group = rank, world, group
+        self.lo, self.hi = block_range(n_total, rank, world)
+        self.device = device
+        self._counts = torch.zeros(L.HQS_MAX_GROUPS, dtype=torch.int32, device=device)
+
+    def add_ready_tasks(self, handles, rq_ids, priorities) -> None:
+        h = np.asarray(handles, dtype=np.int64)
+        # every rank sees the whole call: number the priority levels identically everywhere
+        lv = np.ascontiguousarray(np.unique(np.asarray(priorities, dtype=np.uint64)))
+        self.s._sync_classes()
+        self.s._check(self.s._lib.hqs_levels_add(self.s._ctx, lv.size, L.ptr(lv)))
+        m = (h >= self.lo) & (h < self.hi)
+        if m.any():
+            self.s.add_ready_tasks((h[m] - self.lo).astype(np.uint32), np.asarray(rq_ids)[m], np.asarray(priorities)[m])
+
+    def run_scheduling(self, now: float = 0.0, out_cap: Optional[int] = None):
+        s = self.s
+        s._sync_classes()
+        w = s._worker_structs(now)
+        free = np.ascontiguousarray(s.free)
+        total = np.ascontiguousarray(s.total)
+        blocked = s._blocked_bytes()
+        ng = C.c_uint32(0)
+        s._check(s._lib.hqs_shard_count(s._ctx, w.shape[0], L.ptr(w), L.ptr(free), L.ptr(total),
+                                        L.ptr(blocked) if blocked is not None else None,
+                                        C.c_void_p(self._counts.data_ptr()), self._counts.numel(), C.byref(ng)))
+        counts_all, before = shard_exchange(self._counts, self.rank, self.world, self.group)
+        torch.cuda.synchronize(self.device)
+        cap = out_cap or max(self.hi - self.lo, 1)
+        s._check(s._lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(counts_all.data_ptr()), C.c_void_p(before.data_ptr()), cap))
+        out = np.zeros(cap, dtype=L.assignment_dtype)
+        free_after = np.zeros_like(free)
+        n = C.c_uint32(0)
+        s._check(s._lib.hqs_tick_fetch(s._ctx, cap, L.ptr(out), C.byref(n), L.ptr(free_after)))
+        a = out[: n.value].copy()
+        a["task"] += np.uint32(self.lo)
+        s.free = free_after
+        return a, free_after

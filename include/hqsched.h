@@ -116,6 +116,9 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes);
  * class and priority.  Handles may be new or re-used after the task left the ready set. */
 int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
                    const uint64_t* priority);
+/* Declares priority values before any task carries them.  Needed when the ready set is sharded over
+ * several contexts (every rank must number the priority levels identically); harmless otherwise. */
+int hqs_levels_add(hqs_ctx* ctx, uint32_t n, const uint64_t* priority);
 /* TaskQueue::remove (taskqueue.rs:194-216): cancel / externally assigned tasks leave the ready set. */
 int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task);
 
