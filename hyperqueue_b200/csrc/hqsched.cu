@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
 // write-back per assignment.
 // ------------------------------------------------------------------------------------------------
 constexpr u32 EMIT_SEG_SMEM = 1024;
+constexpr u32 EMIT_ROWS = 4;          // rows of 32 tasks per warp: chunk = warps * 128 task slots
 
 // lanes of the warp holding the same group id, in constant time: one ballot per key bit (match.any
 // iterates once per DISTINCT key, and a warp of 32 tasks holds ~30 distinct (level, class) keys)
@@ -999,20 +1000,26 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
 
     const u32 base = blockIdx.x * chunk;
     const u32 end = min(base + chunk, n_handles);
-    const u32 sub = chunk / nwarps;                  // multiple of 32
-    const u32 wbeg = base + warp * sub;
-    const u32 wend = min(wbeg + sub, end);
+    // every warp owns EMIT_ROWS rows of 32 consecutive tasks; keys and peer masks stay in registers
+    // between the counting pass and the emitting pass
+    const u32 wbeg = base + warp * (32 * EMIT_ROWS);
     u32* mycnt = s_cnt + warp * G;
-
-    // pass 1: per-warp counts
-    for (u32 i = wbeg + lane; i < wbeg + sub; i += 32) {
-        const u32 k = (i < wend) ? __ldg(key + i) : 0u;
-        const bool ready = (k & KEY_READY) != 0;
-        const u32 g = key_level(k) * Q + key_class(k);
+    u32 kk[EMIT_ROWS], gg[EMIT_ROWS], peers[EMIT_ROWS];
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS; ++j) {
+        const u32 i = wbeg + j * 32 + lane;
+        kk[j] = i < end ? key[i] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS; ++j) {
+        const bool ready = (kk[j] & KEY_READY) != 0;
+        gg[j] = key_level(kk[j]) * Q + key_class(kk[j]);
         const u32 act = __ballot_sync(0xffffffffu, ready);
-        const u32 peers = same_key_lanes(act, g, nbits);
-        if (ready && (u32)(__ffs(peers) - 1) == lane) mycnt[g] += __popc(peers);
-        if (i - lane + 32 >= wend) break;   // uniform: whole row past the end
+        peers[j] = same_key_lanes(act, gg[j], nbits);
+        if (!ready) peers[j] = 0;
+        // pass 1: per-warp counts (rows in order; the leader of each key adds its lanes)
+        if (ready && (u32)(__ffs(peers[j]) - 1) == lane) mycnt[gg[j]] += __popc(peers[j]);
+        __syncwarp();
     }
     __syncthreads();
     // turn counts into starting ranks: rank0(w, g) = table[b][g] + sum_{w' < w} cnt[w'][g]
@@ -1028,21 +1035,19 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
     __syncthreads();
 
     // pass 2: rank and emit
-    for (u32 i = wbeg + lane; i < wbeg + sub; i += 32) {
-        const u32 k = (i < wend) ? key[i] : 0u;
-        const bool ready = (k & KEY_READY) != 0;
-        const u32 g = key_level(k) * Q + key_class(k);
-        const u32 act = __ballot_sync(0xffffffffu, ready);
-        const u32 peers = same_key_lanes(act, g, nbits);
-        if (ready) {
-            const u32 leader = __ffs(peers) - 1;
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS; ++j) {
+        const u32 i = wbeg + j * 32 + lane;
+        const u32 k = kk[j], g = gg[j], pm = peers[j];
+        if (pm) {
+            const u32 leader = __ffs(pm) - 1;
             u32 r0 = 0;
             if (leader == lane) {
                 r0 = mycnt[g];
-                mycnt[g] = r0 + __popc(peers);
+                mycnt[g] = r0 + __popc(pm);
             }
-            r0 = __shfl_sync(peers, r0, leader);
-            const u32 r_loc = r0 + __popc(peers & ((1u << lane) - 1));   // rank among this rank's tasks
+            r0 = __shfl_sync(pm, r0, leader);
+            const u32 r_loc = r0 + __popc(pm & ((1u << lane) - 1));      // rank among this rank's tasks
             const u32 bef = before ? __ldg(before + g) : 0u;
             const GroupOut go = g_smem ? s_go[g] : gout[g];
             if (r_loc + bef < go.k) {
@@ -1075,7 +1080,7 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
                 key[i] = (k & ~KEY_READY) | KEY_DONE;                     // Waiting -> Assigned
             }
         }
-        if (i - lane + 32 >= wend) break;
+        __syncwarp();
     }
 }
 
@@ -1401,11 +1406,8 @@ TickGeom tick_geom(const hqs_ctx* ctx) {
     }
     t.g_smem = ((size_t)t.emit_warps * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= EMIT_SMEM_BUDGET) ? 1 : 0;
     t.emit_smem = (size_t)t.emit_warps * t.G * 4 + (t.g_smem ? (size_t)t.G * sizeof(GroupOut) : 0) + seg_cache;
-    const u32 align = 32 * t.emit_warps;
-    const u32 p_max = (t.emit_smem <= 100 * 1024 ? 2u : 1u) * ctx->sm_count;
     const u32 n = std::max<u32>(ctx->n_handles, 1);
-    u32 chunk = (n + p_max - 1) / p_max;
-    chunk = std::max<u32>(align, (chunk + align - 1) / align * align);
+    const u32 chunk = t.emit_warps * 32 * EMIT_ROWS;     // every emit warp owns EMIT_ROWS rows
     t.chunk = chunk;
     t.P = (n + chunk - 1) / chunk;
     return t;
@@ -1490,7 +1492,9 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     // worker, spread over the SMs).  All CTAs must be co-resident (cooperative launch): <= one per SM.
     u32 grid = std::max<u32>(1 + a.scan_ctas, std::min<u32>(ctx->sm_count, 1 + (W + 1) / 2));
     grid = std::min<u32>(grid, ctx->sm_count);
-    a.pack_enabled = (ctx->pack && grid >= 2) ? 1 : 0;
+    static const bool dbg_small_grid = getenv("HQS_DEBUG_SMALL_GRID") != nullptr;   // profiling aid: solver CTA + scan CTAs only
+    if (dbg_small_grid) grid = 1 + a.scan_ctas;
+    a.pack_enabled = (ctx->pack && grid >= 2 && !dbg_small_grid) ? 1 : 0;
     // SMALL variant: class table + variant order staged in shared memory
     a.smem_classes = ((size_t)a.classes_bytes + (size_t)ctx->Q * HQS_MAX_VARIANTS <= 48 * 1024) ? 1 : 0;
     a.smem_vorder = a.smem_classes;
@@ -1561,18 +1565,18 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete ctx;
