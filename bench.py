@@ -298,8 +298,14 @@ def run_cuda(args) -> None:
             "sum_ms": acc[3],
         }
         achieved = bytes_emit / acc[2] / 1e6
+        traffic = None      # dram read + write bytes of one emit_k launch from the committed ncu --set full capture
+        mp = os.path.join(ROOT, "profiles", "r1_ncu_metrics.json")
+        if os.path.exists(mp):
+            m = json.load(open(mp)).get("emit_k")
+            if m and m.get("dram_bytes_read") is not None:
+                traffic = m["dram_bytes_read"] + (m.get("dram_bytes_write") or 0.0)
         roofline = {"bound": "hbm", "kernel": "emit_k", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_task": 16, "note": "interned classes: 4 B key read + 8 B assignment + 4 B key write-back per task "
                                                   "(SURVEY §8(d) budgets 36 B/task for un-interned per-task amounts)",
                     "tick_frac_of_hbm": ((4.0 + 16.0) * N_TASKS / (ms_per_step / 1000.0) / 1e9) / peak}

@@ -53,9 +53,26 @@ def compute_gap_resources(rqv: ResourceRequestVariants, resources: WorkerResourc
 class GapCache:
     def __init__(self) -> None:
         self._cache: Dict[Tuple[int, Tuple[int, ...]], WorkerResources] = {}
+        # memo of the whole (pure) function for workers without assigned tasks: the reference recomputes it
+        # per (cut, blocker, worker) in ~a microsecond of Rust; in Python that loop would dominate the tick
+        self._memo: Dict[Tuple[int, int, Tuple[int, ...]], int] = {}
 
     def get_gap(self, high_rq: int, low_rq: int, resources: WorkerResources,
                 assigned: Iterable[Tuple[int, int]], rq_map: ResourceRqMap) -> int:
+        assigned = list(assigned)
+        mkey = None
+        if not assigned:
+            mkey = (high_rq, low_rq, resources.key())
+            hit = self._memo.get(mkey)
+            if hit is not None:
+                return hit
+        out = self._get_gap(high_rq, low_rq, resources, assigned, rq_map)
+        if mkey is not None:
+            self._memo[mkey] = out
+        return out
+
+    def _get_gap(self, high_rq: int, low_rq: int, resources: WorkerResources,
+                 assigned: Iterable[Tuple[int, int]], rq_map: ResourceRqMap) -> int:
         h_rqv = rq_map.get(high_rq)
         if h_rqv.is_multi_node():
             return 0
