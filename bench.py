@@ -94,8 +94,8 @@ class ClockSampler(threading.Thread):
 
 
 def make_workload(n_tasks: int, seed: int, n_workers: int = N_WORKERS, free_scale: int = FREE_SCALE):
-    import parity as P
-    return P.make_independent(n_tasks, n_workers, N_CLASSES, seed=seed, free_scale=free_scale)
+    import workloads as WL          # synthetic inputs only; does not import the oracle
+    return WL.make_independent(n_tasks, n_workers, N_CLASSES, seed=seed, free_scale=free_scale)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -148,7 +148,7 @@ def run_reference(args) -> None:
 def run_cuda(args) -> None:
     import torch
     import torch.distributed as dist
-    import parity as P
+    import workloads as P           # the CUDA arm never imports oracle/ (only the cpu_baseline leg below does)
     from hyperqueue_b200 import _lib as L, priority_from_user
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
