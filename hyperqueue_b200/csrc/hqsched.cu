@@ -460,39 +460,40 @@ struct ScanOut {
 };
 
 // Block-wide "hand out `remaining` units in worker order": thread (worker) w offers cnt, receives
-// take = clamp(remaining - sum_{w' < w} cnt_{w'}, 0, cnt).  One barrier (double-buffered exchange).
+// take = clamp(remaining - sum_{w' < w} cnt_{w'}, 0, cnt).  One barrier (double-buffered exchange): warp
+// inclusive scan by shuffles, then every thread adds up the (few) warp totals below it serially — 8 loads
+// and adds beat a second 5-step shuffle scan on this latency-bound path.  The rank of a taker among the
+// workers that offer anything comes from a ballot, not from the scan.
 __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u32& parity, u32& seg_rank) {
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     u64* buf = s_x + 32 * (parity & 1);
     parity++;
-    const u64 x = cnt | (cnt ? (1ull << 42) : 0ull);     // low 42 bits count, high bits "has any"
-    u64 inc = x;
+    u64 inc = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
         if ((int)lane >= d) inc += y;
     }
-    if (lane == 31) buf[warp] = inc;
+    const u32 hasb = __ballot_sync(0xffffffffu, cnt != 0);
+    if (lane == 31) buf[warp] = inc | ((u64)__popc(hasb) << 42);       // low 42 bits count, high bits offerers
     __syncthreads();
-    u64 winc = lane < nwarps ? buf[lane] : 0;            // every warp scans the warp totals itself
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const u64 y = __shfl_up_sync(0xffffffffu, winc, d);
-        if ((int)lane >= d) winc += y;
+    u64 below = 0, all = 0;
+    for (u32 w2 = 0; w2 < nwarps; ++w2) {
+        const u64 v = buf[w2];
+        all += v;
+        if (w2 < warp) below += v;
     }
-    const u64 block_total = __shfl_sync(0xffffffffu, winc, 31);
-    const u64 warp_off = warp ? __shfl_sync(0xffffffffu, winc, warp - 1) : 0;
-    const u64 exc = warp_off + inc - x;
     const u64 mask = (1ull << 42) - 1;
+    const u64 exc = (below & mask) + inc - cnt;
     ScanOut o;
-    o.exc_cnt = (u32)((exc & mask) < remaining ? (exc & mask) : remaining);
+    o.exc_cnt = (u32)(exc < remaining ? exc : remaining);
     o.take = 0;
-    if (cnt && (exc & mask) < remaining) {
-        const u64 room = remaining - (exc & mask);
+    if (cnt && exc < remaining) {
+        const u64 room = remaining - exc;
         o.take = (u32)(cnt < room ? cnt : room);
     }
-    seg_rank = (u32)(exc >> 42);
-    o.tot_cnt = block_total & mask;
+    seg_rank = (u32)(below >> 42) + __popc(hasb & ((1u << lane) - 1));
+    o.tot_cnt = all & mask;
     o.n_takers = 0;      // the caller counts the takers (a second barrier that also fences s_x reuse)
     return o;
 }
