@@ -221,6 +221,7 @@ count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32
 //   CTAs >= 1      then wait for CTA 0: if the tick has a saturated level, every worker is filled by its
 //                  own warp (pack_body, alignment heuristic) spread over the whole grid
 // ------------------------------------------------------------------------------------------------
+constexpr u32 SEG_SMEM = 4096;        // count segments buffered in shared memory before a bulk flush
 constexpr u32 PACK_MAX_CAND = 64;    // (class, variant) candidates of the packed level: 2 per lane
 constexpr u32 PACK_MAX_ITER = 64;
 constexpr u32 PACK_CHUNK_DIV = 8;
@@ -530,9 +531,19 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         vorder = a.vorder;
     }
     uint2* s_glist = reinterpret_cast<uint2*>(sp);
-    uint8_t* s_alive = sp + (size_t)a.smem_glist_cap * sizeof(uint2);   // [gl_cap] group still placeable
+    u32* s_gcl = reinterpret_cast<u32*>(sp + (size_t)a.smem_glist_cap * sizeof(uint2));   // [gl_cap] class | level << 16
+    uint8_t* s_alive = sp + (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32));     // [gl_cap] group still placeable
+    // Outputs of the sequential loop are buffered in shared memory and written out in bulk: a global store
+    // in front of a barrier costs an L2 round trip per step (bar.sync waits for the store to be visible).
+    unsigned char* sp2 = sp + (((size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1)) + 15 & ~size_t(15));
+    GroupOut* s_gout = reinterpret_cast<GroupOut*>(sp2);                                   // [gl_cap], by entry
+    u32* s_segc = reinterpret_cast<u32*>(sp2 + (size_t)a.smem_glist_cap * sizeof(GroupOut)); // [SEG_SMEM]
+    u32* s_segw = s_segc + SEG_SMEM;
+    u32 seg_flushed = 0;                                                                    // uniform
     const u32 gl_cap = a.smem_glist_cap;
 #define GL(e) ((e) < gl_cap ? s_glist[(e)] : a.glist[(e)])
+#define GC(e) ((e) < gl_cap ? (s_gcl[(e)] & 0xFFFFu) : (a.glist[(e)].x % a.Q))      /* class of entry e */
+#define GLV(e) ((e) < gl_cap ? (s_gcl[(e)] >> 16) : (a.glist[(e)].x / a.Q))        /* level of entry e */
 
     const long long t_start = clock64();
     long long t_sat = 0, t_groups = 0;
@@ -565,7 +576,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         if (n) {
             const u32 slot = off + __popc(bal & ((1u << lane) - 1));
             a.glist[slot] = make_uint2(g, n);
-            if (slot < gl_cap) s_glist[slot] = make_uint2(g, n);
+            if (slot < gl_cap) { s_glist[slot] = make_uint2(g, n); s_gcl[slot] = (g % a.Q) | ((g / a.Q) << 16); }
         }
         __syncthreads();
         if (tid == 0) {
@@ -576,7 +587,20 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         __syncthreads();
     }
     const u32 n_list = s_nlist;
-    for (u32 e = tid; e < gl_cap; e += blockDim.x) s_alive[e] = 1;
+    for (u32 e = tid; e < gl_cap; e += blockDim.x) {
+        s_alive[e] = 1;
+        GroupOut z; z.k = 0; z.out_off = 0; z.seg_lo = 0; z.seg_n = 0;
+        s_gout[e] = z;
+    }
+#define FLUSH_SEGMENTS_IF_FULL()                                                                      \
+    if (seg_base - seg_flushed + blockDim.x > SEG_SMEM) {                                             \
+        for (u32 i_ = tid; i_ < seg_base - seg_flushed; i_ += blockDim.x) {                          \
+            a.seg_cum[seg_flushed + i_] = s_segc[i_];                                                 \
+            a.seg_wv[seg_flushed + i_] = s_segw[i_];                                                  \
+        }                                                                                             \
+        __syncthreads();                                                                              \
+        seg_flushed = seg_base;                                                                       \
+    }
     // groups without ready tasks keep k = 0 (emit_k's chunk filter reads k of every group)
     for (u32 g = tid; g < a.G; g += blockDim.x) a.gout[g].k = 0;
     __syncthreads();
@@ -591,9 +615,9 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     u32 li = 0;
     while (li < n_list) {
         // ---- one priority level: entries [li, lj)
-        const u32 lvl = GL(li).x / a.Q;
+        const u32 lvl = GLV(li);
         u32 lj = li + 1;
-        while (lj < n_list && GL(lj).x / a.Q == lvl) ++lj;
+        while (lj < n_list && GLV(lj) == lvl) ++lj;
         const u32 ng = lj - li;
         bool level_packed = false;
         const long long t_l0 = clock64();
@@ -609,7 +633,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             val[2 * RT] = 0;
             if (tid < ng) {
                 const uint2 ge = GL(li + tid);
-                const u32 c = ge.x % a.Q;
+                const u32 c = GC(li + tid);
                 const u32 nvv = classes[c].n_variants;
                 u64 flag = 0;
                 for (u32 v = 0; v < nvv; ++v) flag |= classes[c].v[v].all_mask ? (1ull << 32) : 0ull;
@@ -658,7 +682,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     // ---- a. quotas: share of each class proportional to how many fit on the worker alone
                     for (u32 e = li; e < lj; ++e) {
                         const uint2 ge = GL(e);
-                        const u32 c = ge.x % a.Q, n = ge.y;
+                        const u32 c = GC(e), n = ge.y;
                         const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
                         u64 cn = 0;
                         if (has_worker)
@@ -691,7 +715,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (tid == 0) {
                         u32 ci = 0;
                         for (u32 e = li; e < lj; ++e) {
-                            const u32 c = GL(e).x % a.Q;
+                            const u32 c = GC(e);
                             for (u32 v = 0; v < classes[c].n_variants; ++v) a.pk.cand[ci++] = c | (v << 16) | ((e - li) << 24);
                         }
                         a.pk.meta[0] = ci;
@@ -730,18 +754,19 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         bool level_unsatisfied = false;
         for (u32 e = li; e < lj; ++e) {
             if (e < gl_cap && !s_alive[e]) {                  // no worker can take a single task of it (uniform)
-                if (level_packed) cand_base += classes[GL(e).x % a.Q].n_variants;
+                if (level_packed) cand_base += classes[GC(e)].n_variants;
                 continue;
             }
             const uint2 ge = GL(e);
             const u32 g = ge.x, n_all = ge.y;
-            const u32 c = g % a.Q;
+            const u32 c = GC(e);
             const u32 nv = classes[c].n_variants;
             u32 remaining = n_all;
             const u32 seg_lo = seg_base;
             const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
             if (level_packed) {
                 for (u32 v = 0; v < nv; ++v) {
+                    FLUSH_SEGMENTS_IF_FULL();
                     const u64 cnt = has_worker ? __ldcg(a.pk.taken + (size_t)tid * PACK_MAX_CAND + cand_base + v) : 0;
                     u32 seg_rank;
                     ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
@@ -749,8 +774,8 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (o.take) {
                         const u32 si = seg_base + seg_rank;
                         if (si < SEG_CAP) {
-                            a.seg_cum[si] = (n_all - remaining) + o.exc_cnt + o.take;
-                            a.seg_wv[si] = tid | (v << 16);
+                            s_segc[si - seg_flushed] = (n_all - remaining) + o.exc_cnt + o.take;
+                            s_segw[si - seg_flushed] = tid | (v << 16);
                         }
                     }
                     if (cnt > o.take) {
@@ -769,24 +794,12 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
                 const u32 v = vorder[c * HQS_MAX_VARIANTS + vi];
                 const VarT<RT>& dv = classes[c].v[v];
-                // can1: at least one task fits; canAll: all that is left fits (no division: compares and
-                // one multiply per resource).  The exact count is only needed when the block-wide scan runs.
-                bool can1 = false, can_all = false;
-                if (has_worker && admissible(dv, v, blk, rem_time)) {
-                    can1 = can_all = true;
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        if (!((dv.used_mask >> r) & 1)) continue;
-                        if ((dv.all_mask >> r) & 1) {
-                            const bool ok = tot[r] != 0 && fr[r] == tot[r];
-                            can1 &= ok; can_all &= ok && remaining <= 1;
-                        } else if (fr[r] != HQS_AMOUNT_MAX) {
-                            can1 &= dv.amount[r] <= fr[r];
-                            can_all &= __umul64hi(dv.amount[r], (u64)remaining) == 0 && dv.amount[r] * (u64)remaining <= fr[r];
-                        }
-                    }
-                    can_all &= can1;
-                }
+                FLUSH_SEGMENTS_IF_FULL();
+                // exact count once (reciprocal division, capped at `remaining`): can1 = cnt > 0, and the
+                // first worker takes everything iff its cnt == remaining
+                u64 cnt = 0;
+                if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, dv, remaining);
+                const bool can1 = cnt != 0, can_all = cnt >= remaining;
                 u32 take = 0, exc_cnt = 0, seg_rank = 0, n_takers = 0, handed = 0;
                 {
                     u64* fb = s_f + 32 * (parity & 1);
@@ -805,7 +818,6 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                             take = (warp == wf && lane == first && can1) ? remaining : 0;
                             n_takers = 1; handed = remaining;
                         } else {
-                            const u64 cnt = can1 ? fit_count<RT>(fr, tot, dv, remaining) : 0;
                             ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
                             take = o.take; exc_cnt = o.exc_cnt;
                             n_takers = (u32)__syncthreads_count(o.take != 0);
@@ -816,8 +828,8 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 if (take) {
                     const u32 si = seg_base + seg_rank;
                     if (si < SEG_CAP) {
-                        a.seg_cum[si] = (n_all - remaining) + exc_cnt + take;
-                        a.seg_wv[si] = tid | (v << 16);
+                        s_segc[si - seg_flushed] = (n_all - remaining) + exc_cnt + take;
+                        s_segw[si - seg_flushed] = tid | (v << 16);
                     }
                     take_from<RT>(fr, dv, take);
                 }
@@ -837,7 +849,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             if (tid == 0) {
                 GroupOut go;
                 go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_base - seg_lo;
-                a.gout[g] = go;
+                if (e < gl_cap) s_gout[e] = go; else a.gout[g] = go;
             }
             out_base += k_loc;
         }
@@ -847,7 +859,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         if (level_unsatisfied && lj < n_list && n_list <= gl_cap) {
             for (u32 e = lj; e < n_list; ++e) {
                 if (!s_alive[e]) continue;                                     // uniform
-                const u32 c = s_glist[e].x % a.Q;
+                const u32 c = GC(e);
                 const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
                 bool can = false;
                 if (has_worker)
@@ -875,6 +887,12 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     }
     const long long t_loop = clock64();
 
+    // ---- flush the buffered segments and per-group records
+    for (u32 i = tid; i < seg_base - seg_flushed; i += blockDim.x) {
+        a.seg_cum[seg_flushed + i] = s_segc[i];
+        a.seg_wv[seg_flushed + i] = s_segw[i];
+    }
+    for (u32 e = tid; e < n_list && e < gl_cap; e += blockDim.x) a.gout[s_glist[e].x] = s_gout[e];
     // ---- epilogue: let the other CTAs go, header, free vectors after the tick, reset the counters
     if (tid == 0 && !signalled) st_release(&a.sync->phase, PHASE_EXIT);
     if (has_worker) {
@@ -893,6 +911,9 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     __syncthreads();
     for (u32 g = tid; g < a.G; g += blockDim.x) a.total_local[g] = 0;
 #undef GL
+#undef GC
+#undef GLV
+#undef FLUSH_SEGMENTS_IF_FULL
 }
 
 template <int RT, int MAXT, bool SMALL>
@@ -1502,7 +1523,8 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     size_t solve_smem = 0;
     if (a.smem_classes) solve_smem += ((a.classes_bytes + 15u) & ~15u) + ((ctx->Q * HQS_MAX_VARIANTS + 15u) & ~15u);
     a.smem_glist_cap = std::min<u32>(t.G, 2048);
-    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + 1) + 16;
+    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + 32;
+    solve_smem += (size_t)a.smem_glist_cap * sizeof(GroupOut) + 2 * SEG_SMEM * sizeof(u32);
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
     void* kargs[] = {&a};
     const bool small = a.smem_classes != 0;

@@ -1,0 +1,131 @@
+"""Edge cases of the CUDA path through the C ABI: maximum sizes (1024 workers, 16 resource kinds, 8 variants),
+large class tables (global-memory class path), more (level x class) groups than HQS_MAX_GROUPS, handle re-use,
+class-table growth, empty capacity, and the error contract (no partial results, ready set unchanged)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import greedy_model as G
+import parity as P
+
+pytestmark = pytest.mark.gpu
+FR = P.FR
+
+
+def _random_workload(n, w, q, r, vmax, seed, n_prio=5, cap=(8, 64)):
+    rng = np.random.default_rng(seed)
+    classes = []
+    seen = set()
+    while len(classes) < q:
+        vs = []
+        for _ in range(int(rng.integers(1, vmax + 1))):
+            k = int(rng.integers(1, min(r, 4) + 1))
+            rs = rng.choice(r, size=k, replace=False)
+            vs.append({"amounts": {int(x): int(rng.integers(1, 9)) * FR // int(rng.choice([1, 2, 4])) for x in rs}})
+        key = repr([sorted(d["amounts"].items()) for d in vs])
+        if key not in seen:
+            seen.add(key); classes.append(vs)
+    total = (rng.integers(cap[0], cap[1], size=(w, r)).astype(np.uint64)) * np.uint64(FR)
+    return P.Workload(r, classes, total, total.copy(), rng.integers(0, q, n).astype(np.uint32),
+                      rng.integers(0, n_prio, n).astype(np.int32))
+
+
+def _check_exact(wl):
+    s = P.gpu_scheduler(wl)
+    fb = s.free.copy()
+    m = s.run_scheduling()
+    assert P.judge_tick(wl, fb, m.assignments).ok
+    exp, exp_free = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), fb)
+    assert np.array_equal(m.assignments, exp)
+    assert np.array_equal(m.free_after, exp_free)
+    s.close()
+    return m
+
+
+def test_maximum_workers_resources_variants():
+    m = _check_exact(_random_workload(30000, 1024, 12, 16, 8, seed=1))
+    assert m.n_assigned() > 1000
+
+
+def test_eight_resources_path():
+    _check_exact(_random_workload(20000, 100, 10, 7, 3, seed=2))
+
+
+def test_large_class_table_uses_global_class_path():
+    # 1500 classes x 648 B > the shared-memory budget of the solver => ClassT read from global memory
+    m = _check_exact(_random_workload(40000, 64, 1500, 4, 1, seed=3, n_prio=2))
+    assert m.n_assigned() > 100
+
+
+def test_more_groups_than_the_limit_are_coarsened():
+    wl = _random_workload(60000, 128, 300, 4, 2, seed=4, n_prio=40)      # 300 x 40 = 12000 groups > 4096
+    s = P.gpu_scheduler(wl)
+    fb = s.free.copy()
+    m = s.run_scheduling()
+    assert s.stats()["coarsened"] == 1 and m.n_assigned() > 100
+    assert P.judge_tick(wl, fb, m.assignments).ok
+    # coarsening merges adjacent levels but never inverts the order of far-apart priorities:
+    pr = wl.task_user_priority[m.assignments["task"]]
+    assert pr[: max(1, pr.size // 10)].mean() >= pr[-max(1, pr.size // 10):].mean()
+    s.close()
+
+
+def test_handle_reuse_and_class_table_growth():
+    from hyperqueue_b200 import RequestVariant, priority_from_user
+    wl = P.make_independent(3000, 8, 4, seed=5)
+    s = P.gpu_scheduler(wl)
+    first = s.run_scheduling()
+    assert first.n_assigned() > 0
+    s.tasks_finished(first.assignments["task"])
+    # a new class appears after tasks were pushed (ResourceRqMap is append-only) ...
+    new_c = s.get_or_create_resource_rq_id([RequestVariant.of({0: 1 * FR})])
+    assert new_c == len(wl.classes)
+    # ... and the finished handles are re-used for tasks of that class with a higher priority than everything
+    h = first.assignments["task"][:50].copy()
+    s.add_ready_tasks(h, np.full(h.size, new_c, dtype=np.uint32), priority_from_user(np.full(h.size, 100)))
+    second = s.run_scheduling()
+    got = set(second.assignments["task"].tolist())
+    assert set(h.tolist()) <= got                        # top priority, 1 cpu each: all placed
+    assert (second.assignments["task"][: h.size] == np.sort(h)).all()   # and emitted first, in handle order
+    s.close()
+
+
+def test_no_capacity_no_assignment_and_ready_set_kept():
+    wl = P.make_independent(2000, 4, 3, seed=6)
+    wl.worker_free = np.zeros_like(wl.worker_free)
+    s = P.gpu_scheduler(wl)
+    assert s.run_scheduling().n_assigned() == 0
+    s.free = wl.worker_total.copy()                      # resources come back: the same ready set is still there
+    assert s.run_scheduling().n_assigned() > 0
+    s.close()
+
+
+def test_error_contract():
+    from hyperqueue_b200 import GpuScheduler, HqsError, RequestVariant, _lib as L, priority_from_user
+    with pytest.raises(HqsError):
+        GpuScheduler(17)                                  # > HQS_MAX_RESOURCES
+    s = GpuScheduler(2)
+    with pytest.raises(HqsError):                         # tick before any class exists
+        s.new_worker(1, [4 * FR, 0]); s.run_scheduling()
+    s.get_or_create_resource_rq_id([RequestVariant.of({0: 1 * FR})])
+    with pytest.raises(HqsError):                         # class id out of range
+        s.add_ready_tasks(np.arange(3, dtype=np.uint32), np.array([0, 1, 0], dtype=np.uint32), priority_from_user(np.zeros(3)))
+    s.add_ready_tasks(np.arange(3, dtype=np.uint32), np.zeros(3, dtype=np.uint32), priority_from_user(np.zeros(3)))
+    # unsorted / duplicate worker ids are rejected before anything is launched; the ready set is untouched
+    w = s._worker_structs(0.0)
+    w2 = np.concatenate([w, w])
+    free = np.ascontiguousarray(np.concatenate([s.free, s.free])); tot = np.ascontiguousarray(np.concatenate([s.total, s.total]))
+    out = np.zeros(8, dtype=L.assignment_dtype); n = C.c_uint32(0)
+    rc = s._lib.hqs_tick(s._ctx, 2, L.ptr(w2), L.ptr(free), L.ptr(tot), None, 8, L.ptr(out), C.byref(n), None)
+    assert rc == -1 and n.value == 0
+    assert s.run_scheduling().n_assigned() == 3
+    # a request that uses a resource the context does not have is refused by hqs_classes_set
+    s2 = GpuScheduler(1)
+    cls = (L.hqs_class * 1)()
+    cls[0].n_variants = 1
+    cls[0].variants[0].amount[1] = 1 * FR
+    cls[0].variants[0].weight = 10000
+    assert s2._lib.hqs_classes_set(s2._ctx, 1, cls) == -1
+    assert b"n_resources" in s2._lib.hqs_last_error(s2._ctx)
+    s.close(); s2.close()
