@@ -594,6 +594,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     }
 #define FLUSH_SEGMENTS_IF_FULL()                                                                      \
     if (seg_base - seg_flushed + blockDim.x > SEG_SMEM) {                                             \
+        __syncthreads();                                                                              \
         for (u32 i_ = tid; i_ < seg_base - seg_flushed; i_ += blockDim.x) {                          \
             a.seg_cum[seg_flushed + i_] = s_segc[i_];                                                 \
             a.seg_wv[seg_flushed + i_] = s_segw[i_];                                                  \
@@ -888,6 +889,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     const long long t_loop = clock64();
 
     // ---- flush the buffered segments and per-group records
+    __syncthreads();
     for (u32 i = tid; i < seg_base - seg_flushed; i += blockDim.x) {
         a.seg_cum[seg_flushed + i] = s_segc[i];
         a.seg_wv[seg_flushed + i] = s_segw[i];
