@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from parity import FR, MAXV, Workload
+from workloads import FR, MAXV, Workload
 
 AMOUNT_MAX = (1 << 64) - 1
 TIME_INF = (1 << 64) - 1

@@ -129,3 +129,28 @@ def test_error_contract():
     assert s2._lib.hqs_classes_set(s2._ctx, 1, cls) == -1
     assert b"n_resources" in s2._lib.hqs_last_error(s2._ctx)
     s.close(); s2.close()
+
+
+def test_min_utilization_vectors():
+    """test_schedule_min_utilization1/2 (test_scheduler_sn.rs:1391-1445) through the shim's post-filter."""
+    from hyperqueue_b200 import GpuScheduler, RequestVariant, priority_from_user
+
+    def run(n_tasks, w_cpus, mu, running_cpus=0):
+        s = GpuScheduler(1)
+        c = s.get_or_create_resource_rq_id([RequestVariant.of({0: 3 * FR})])
+        s.new_worker(1, [w_cpus * FR], min_utilization=mu, free=[(w_cpus - running_cpus) * FR])
+        s.add_ready_tasks(np.arange(n_tasks, dtype=np.uint32), np.full(n_tasks, c, dtype=np.uint32), priority_from_user(np.zeros(n_tasks)))
+        m = s.run_scheduling()
+        again = s.run_scheduling().n_assigned() if m.n_assigned() == 0 else None
+        free = s.free.copy()
+        s.close()
+        return m.n_assigned(), again, free
+
+    assert run(2, 9, 1.0)[0] == 0
+    assert run(3, 9, 1.0)[0] == 3
+    assert run(2, 9, 1.0, running_cpus=3)[0] == 2
+    for n, mu, exp in [(2, 0.5, 2), (2, 0.51, 0), (3, 0.51, 3), (3, 0.75, 3), (3, 0.76, 0)]:
+        got, again, free = run(n, 12, mu)
+        assert got == exp, (n, mu, got)
+        if exp == 0:
+            assert again == 0 and int(free[0, 0]) == 12 * FR      # dropped tasks are ready again; nothing leaked
