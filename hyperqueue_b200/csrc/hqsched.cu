@@ -300,14 +300,14 @@ __device__ __forceinline__ void st_release(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// floor(n / d) for d > 0 with the precomputed reciprocal; exact (the estimate is off by at most one)
-__device__ __forceinline__ u64 div_floor(u64 n, u64 d, double rcp) {
-    if (n >> 53) return n / d;
-    u64 q = (u64)__double2ull_rz(__dmul_rn(__ull2double_rn(n), rcp));
-    const u64 p = q * d;
-    if (p > n) --q;
-    else if (n - p >= d) ++q;
-    return q;
+// min(cap, floor(n / d)) for d > 0, cap < 2^32.  FP64 conversions of 64-bit integers cost hundreds of cycles
+// on this part (measured: ~270 cycles per reciprocal division), so: (1) if cap * d <= n the resource does not
+// constrain at all — one multiply and a compare, the common case while capacity exceeds demand; (2) operands
+// below 2^32 use the 32-bit divider; (3) only huge operands with a binding constraint pay a 64-bit division.
+__device__ __forceinline__ u64 div_cap(u64 n, u64 d, u64 cap) {
+    if (__umul64hi(d, cap) == 0 && d * cap <= n) return cap;
+    if (((n | d) >> 32) == 0) return (u64)((u32)n / (u32)d);
+    return n / d;
 }
 
 template <int RT>
@@ -327,7 +327,7 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
         if (!((used >> r) & 1)) continue;
         u64 q;
         if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
-        else if (fr[r] != HQS_AMOUNT_MAX) q = div_floor(fr[r], dv.amount[r], dv.rcp[r]);
+        else if (fr[r] != HQS_AMOUNT_MAX) q = div_cap(fr[r], dv.amount[r], cnt);
         else continue;
         cnt = cnt < q ? cnt : q;
     }
