@@ -231,7 +231,7 @@ constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: a stuck grid 
 template <int RT>
 struct VarT {
     u64 amount[RT];
-    double rcp[RT];      // 1.0 / amount (0 where unused): floor(free / amount) without a 64-bit divide
+    float rcpf[2 * RT];  // [0, RT): fp32 1.0 / amount (0 where unused) for the quotient estimate; rest: padding
     u64 min_time_ms;
     u32 all_mask;
     u32 used_mask;
@@ -300,13 +300,27 @@ __device__ __forceinline__ void st_release(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// min(cap, floor(n / d)) for d > 0, cap < 2^32.  FP64 conversions of 64-bit integers cost hundreds of cycles
-// on this part (measured: ~270 cycles per reciprocal division), so: (1) if cap * d <= n the resource does not
-// constrain at all — one multiply and a compare, the common case while capacity exceeds demand; (2) operands
-// below 2^32 use the 32-bit divider; (3) only huge operands with a binding constraint pay a 64-bit division.
-__device__ __forceinline__ u64 div_cap(u64 n, u64 d, u64 cap) {
+// min(cap, floor(n / d)) for d > 0, cap < 2^32, exact.  64-bit divisions (software routine, or FP64 reciprocals
+// with 64-bit int<->double conversions) cost several hundred cycles each and sit on the solver's sequential
+// critical path once per resource, so:
+//  (1) cap * d <= n  -> the resource does not constrain: one multiply and a compare (capacity >> demand);
+//  (2) quotient below 2^20 -> fp32 estimate from the precomputed reciprocal (the 64-bit operand is converted
+//      through its two 32-bit halves), then an exact integer fix-up of at most +-2;
+//  (3) anything else (a single worker taking more than a million tasks of one group) -> 64-bit division.
+__device__ __forceinline__ u64 div_cap(u64 n, u64 d, float rcpf, u64 cap) {
     if (__umul64hi(d, cap) == 0 && d * cap <= n) return cap;
-    if (((n | d) >> 32) == 0) return (u64)((u32)n / (u32)d);
+    const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
+    const float qf = nf * rcpf;
+    if (qf < 1048576.0f) {
+        u64 q = (u64)__float2uint_rz(qf);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const u64 p = q * d;
+            if (p > n) --q;
+            else if (n - p >= d) ++q;
+        }
+        return q;
+    }
     return n / d;
 }
 
@@ -327,7 +341,7 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
         if (!((used >> r) & 1)) continue;
         u64 q;
         if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
-        else if (fr[r] != HQS_AMOUNT_MAX) q = div_cap(fr[r], dv.amount[r], cnt);
+        else if (fr[r] != HQS_AMOUNT_MAX) q = div_cap(fr[r], dv.amount[r], dv.rcpf[r], cnt);
         else continue;
         cnt = cnt < q ? cnt : q;
     }
@@ -1648,7 +1662,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
         for (u32 v = 0; v < sc.n_variants; ++v) {
             unsigned char* vb = cb + 8 + (size_t)v * var_bytes;
             u64* amount = reinterpret_cast<u64*>(vb);
-            double* rcp = reinterpret_cast<double*>(vb + (size_t)RT * 8);
+            float* rcp = reinterpret_cast<float*>(vb + (size_t)RT * 8);
             u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 16);
             u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 16 + 8);
             u32 used = 0;
@@ -1659,7 +1673,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                     return fail(ctx, HQS_E_INVALID, "class %u variant %u uses resource %u >= n_resources", c, v, r);
                 if (r < RT) {
                     amount[r] = all ? 0 : amt;
-                    rcp[r] = (!all && amt) ? 1.0 / (double)amt : 0.0;
+                    rcp[r] = (!all && amt) ? 1.0f / (float)amt : 0.0f;
                 }
                 if (all || amt) used |= 1u << r;
             }
