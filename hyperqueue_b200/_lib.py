@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "hqs_abi_version", "hqs_create", "hqs_destroy", "hqs_last_error", "hqs_classes_set", "hqs_ready_push",
     "hqs_ready_remove", "hqs_dag_load", "hqs_tasks_finished", "hqs_tick", "hqs_tick_launch", "hqs_tick_fetch",
     "hqs_shard_count", "hqs_shard_solve_emit", "hqs_device_result", "hqs_ready_rearm", "hqs_stream", "hqs_sync",
-    "hqs_get_stats", "hqs_set_stream", "hqs_set_profile", "hqs_get_kernel_ms", "hqs_debug_read", "hqs_levels_add",
+    "hqs_get_stats", "hqs_set_stream", "hqs_set_profile", "hqs_get_kernel_ms", "hqs_debug_read", "hqs_levels_add", "hqs_query",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.hqs_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.hqs_debug_read.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.hqs_levels_add.argtypes = [vp, u32, u64p]
+    lib.hqs_query.argtypes = [vp, u32, vp, u64p, u64p, u8p, C.POINTER(C.c_uint32), u32p, u64p]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int or name in ("hqs_abi_version",):

@@ -1122,6 +1122,23 @@ emit_k(u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32 g_smem
     }
 }
 
+// per-worker totals of the count segments (what-if query)
+__global__ void seg_worker_totals_k(const TickHeaderOut* __restrict__ hdr, const GroupOut* __restrict__ gout, u32 G,
+                                    const u32* __restrict__ seg_cum, const u32* __restrict__ seg_wv, u32* __restrict__ per_worker) {
+    // one thread per group: walks the group's segments (inclusive end ranks -> counts)
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const GroupOut go = gout[g];
+    if (go.k == 0) return;
+    u32 prev = 0;
+    for (u32 i = 0; i < go.seg_n; ++i) {
+        const u32 end = seg_cum[go.seg_lo + i];
+        atomicAdd(&per_worker[seg_wv[go.seg_lo + i] & 0xFFFFu], end - prev);
+        prev = end;
+    }
+    (void)hdr;
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -1500,7 +1517,7 @@ int launch_count(hqs_ctx* ctx, const TickGeom& t) {
 }
 
 int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, bool blocked,
-                      const u32* d_counts_all, const u32* d_before, u32 out_cap) {
+                      const u32* d_counts_all, const u32* d_before, u32 out_cap, bool no_emit = false) {
     SolveArgs a;
     a.free_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_free);
     a.total_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_total);
@@ -1554,6 +1571,7 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     else CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
     ctx->stats.kernel_launches++;
     if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (!no_emit)
     emit_k<<<t.P, 32 * t.emit_warps, t.emit_smem, ctx->stream>>>(
         ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, t.g_smem, t.nbits, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
         ctx->d_seg_wv, ctx->d_hdr, ctx->d_out, out_cap);
@@ -1943,6 +1961,46 @@ int hqs_tick(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const 
     int rc = hqs_tick_launch(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, out_cap);
     if (rc) return rc;
     return hqs_tick_fetch(ctx, out_cap, out, out_n, free_after);
+}
+
+int hqs_query(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+              const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t* n_would_assign,
+              uint32_t* per_worker_assigned, uint64_t* free_after) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n_would_assign) *n_would_assign = 0;
+    int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
+    if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, 1024))) return rc;
+    TickLayout lay;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
+    if (ctx->n_handles == 0) {
+        if (per_worker_assigned) memset(per_worker_assigned, 0, n_workers * sizeof(u32));
+        if (free_after) memcpy(free_after, free_rw, (size_t)n_workers * ctx->R * 8);
+        return HQS_OK;
+    }
+    if ((rc = launch_count(ctx, t))) return rc;
+    if ((rc = launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, 0, true))) return rc;
+    ctx->tick_pending = false;      // nothing was emitted or consumed
+    ctx->stats.ticks--;
+    u32* d_pw = ctx->d_pk_quota;    // scratch (pack is over): [W] counters
+    CU(cudaMemsetAsync(d_pw, 0, n_workers * sizeof(u32), ctx->stream));
+    seg_worker_totals_k<<<(t.G + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hdr, ctx->d_gout, t.G, ctx->d_seg_cum, ctx->d_seg_wv, d_pw);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    TickHeaderOut hdr;
+    std::vector<u32> pw(n_workers);
+    CU(cudaMemcpyAsync(&hdr, ctx->d_hdr, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(pw.data(), d_pw, n_workers * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (free_after) CU(cudaMemcpyAsync(free_after, ctx->d_free_after, (size_t)n_workers * ctx->R * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (hdr.error == 2) return fail(ctx, HQS_E_CUDA, "solver grid synchronisation timed out");
+    if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow");
+    if (n_would_assign) *n_would_assign = hdr.n_assigned;
+    if (per_worker_assigned) memcpy(per_worker_assigned, pw.data(), n_workers * sizeof(u32));
+    return HQS_OK;
 }
 
 int hqs_shard_count(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,

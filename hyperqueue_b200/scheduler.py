@@ -337,6 +337,20 @@ class GpuScheduler:
             return int(n_new.value)
         return 0
 
+    def new_worker_query(self, worker_totals: np.ndarray, now: float = 0.0):
+        """compute_new_worker_query (scheduler/query.rs:12-131): which of these HYPOTHETICAL workers would get
+        work from the current ready set?  Nothing is consumed.  Returns (needed[bool], counts, total)."""
+        self._sync_classes()
+        tot = np.ascontiguousarray(worker_totals, dtype=np.uint64)
+        nw = tot.shape[0]
+        w = np.zeros(nw, dtype=L.worker_dtype)
+        w["worker_id"] = np.arange(nw, dtype=np.uint32)
+        w["remaining_time_ms"] = np.uint64(L.HQS_TIME_INF)
+        counts = np.zeros(nw, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self._check(self._lib.hqs_query(self._ctx, nw, L.ptr(w), L.ptr(tot), L.ptr(tot), None, C.byref(n), L.ptr(counts), None))
+        return counts > 0, counts, int(n.value)
+
     # misc ---------------------------------------------------------------------------------------
     def rearm(self) -> None:
         self._check(self._lib.hqs_ready_rearm(self._ctx))

@@ -156,6 +156,15 @@ int hqs_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
 int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t* out_n,
                    uint64_t* free_after);
 
+/* What-if query (scheduler/query.rs:12-131, ServerRef::new_worker_query control.rs:123-136): runs the histogram
+ * and the solver against an arbitrary (e.g. hypothetical, autoalloc) worker array WITHOUT emitting or consuming
+ * anything: the ready set is unchanged.  per_worker_assigned[n_workers] (optional) receives how many tasks each
+ * worker would get — a fake worker is "needed" iff its count is > 0; free_after as in hqs_tick.  Partial
+ * descriptors use HQS_AMOUNT_MAX for unknown resources (query.rs:35-46). */
+int hqs_query(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+              const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t* n_would_assign,
+              uint32_t* per_worker_assigned, uint64_t* free_after);
+
 /* Multi-GPU sharding: each rank owns a contiguous handle range of the task table.
  * Phase 1 counts the rank's ready tasks per group into d_counts (device pointer, n_groups_cap u32).
  * The host all-gathers the count vectors (NCCL), then phase 2 runs the replicated deterministic solve

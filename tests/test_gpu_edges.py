@@ -154,3 +154,19 @@ def test_min_utilization_vectors():
         assert got == exp, (n, mu, got)
         if exp == 0:
             assert again == 0 and int(free[0, 0]) == 12 * FR      # dropped tasks are ready again; nothing leaked
+
+
+def test_new_worker_query_is_a_dry_run():
+    """Shape of test_query.rs: fake workers, partial descriptors with MAX, nothing consumed."""
+    wl = P.make_independent(3000, 4, 4, seed=12)
+    s = P.gpu_scheduler(wl)
+    fake = np.array([[128 * FR, 8 * FR, 512 * FR, 2048 * FR],            # a full node
+                     [1 * FR, 0, 1 * FR, 0],                              # too small for anything
+                     [64 * FR, P.J.AMOUNT_MAX, P.J.AMOUNT_MAX, P.J.AMOUNT_MAX]], dtype=np.uint64)   # partial descriptor
+    needed, counts, total = s.new_worker_query(fake)
+    assert needed.tolist() == [True, False, True] and total == int(counts.sum()) and counts[0] > 0
+    again = s.new_worker_query(fake)
+    assert np.array_equal(again[1], counts)                              # a query consumes nothing
+    real = s.run_scheduling()
+    assert real.n_assigned() > 0                                          # and the real tick still sees every task
+    s.close()
