@@ -517,6 +517,7 @@ template <int RT, bool SMALL>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     __shared__ u64 s_x[64], s_f[64];
     __shared__ u64 s_red[2 * 32 * (2 * RT + 1)];
+    __shared__ u64 s_totmax[RT];
     __shared__ u32 s_a[40], s_b[40];
     __shared__ u32 s_nlist;
     const u32 tid = threadIdx.x;
@@ -568,6 +569,26 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         tot[r] = (has_worker && r < (int)a.R) ? a.total_rw[(size_t)tid * a.R + r] : 0;
     }
     const u64 rem_time = has_worker ? a.rem_time[tid] : 0;
+    // per-resource maximum of the worker totals (a class no worker is big enough for is not demand)
+    {
+        u64 m[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            m[r] = tot[r];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) { const u64 y = __shfl_xor_sync(0xffffffffu, m[r], d); m[r] = y > m[r] ? y : m[r]; }
+        }
+        if (lane == 0)
+#pragma unroll
+            for (int r = 0; r < RT; ++r) s_red[warp * RT + r] = m[r];
+        __syncthreads();
+        if (tid < RT) {
+            u64 best = 0;
+            for (u32 w2 = 0; w2 < nwarps; ++w2) best = s_red[w2 * RT + tid] > best ? s_red[w2 * RT + tid] : best;
+            s_totmax[tid] = best;
+        }
+        __syncthreads();
+    }
 
     // ---- compact the non-empty groups, in processing order: level asc (= priority desc), then the
     //      tick's class order
@@ -654,10 +675,13 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 for (u32 v = 0; v < nvv; ++v) flag |= classes[c].v[v].all_mask ? (1ull << 32) : 0ull;
                 val[2 * RT] = nvv | flag;                                  // low: candidates, bit 32+: has `All`
                 const VarT<RT>& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
+                bool servable = true;
+#pragma unroll
+                for (int r = 0; r < RT; ++r) servable &= dv.amount[r] <= s_totmax[r];
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const u64 hi = __umul64hi(dv.amount[r], (u64)ge.y);
-                    val[RT + r] = hi ? HQS_AMOUNT_MAX : dv.amount[r] * (u64)ge.y;
+                    val[RT + r] = !servable ? 0 : (hi ? HQS_AMOUNT_MAX : dv.amount[r] * (u64)ge.y);
                 }
             }
 #pragma unroll

@@ -153,9 +153,13 @@ def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[Li
             if s == U64:
                 break
         C[r] = s
+    tot_max = [max(t.tot[w][r] for w in range(W)) for r in range(R)]
     D = [0] * R
     for c, n in groups:
-        for r, a in t.am[c][vorder[c][0]].items():
+        am = t.am[c][vorder[c][0]]
+        if any(a > tot_max[r] for r, a in am.items()):
+            continue            # no worker is big enough for it: it is not demand that capacity could serve
+        for r, a in am.items():
             D[r] = _sat_add(D[r], _sat_mul(n, a))
     return any(C[r] != U64 and D[r] > C[r] for r in range(R))
 

@@ -1,8 +1,7 @@
 """The reference's own known-answer vectors (tests/vectors.py, transcribed from test_scheduler_sn.rs) run
 through the device algorithm: its sequential specification on CPU, the CUDA path on the GPU.
 
-40 of the 44 single-tick vectors are reproduced exactly.  The 4 documented deviations:
-  nop-9            the saturated level is spread over workers by the packing step, the MILP compacts (4+1 vs 3+2)
+41 of the 44 single-tick vectors are reproduced exactly.  The 3 documented deviations:
   prio-6-all-four  the MILP finds the one arrangement that places all four tasks, first-fit places three
   prio-10, prio-11 the reference's priority cut keeps a lower-priority 1-cpu task out of the gap a waiting
                    2-cpu class could use (gap.rs); gap/reservation semantics are not implemented on the device
@@ -13,7 +12,7 @@ import pytest
 import greedy_model as G
 import vectors as V
 
-KNOWN_DEVIATIONS = {"nop-9", "prio-6-all-four", "prio-10", "prio-11"}
+KNOWN_DEVIATIONS = {"prio-6-all-four", "prio-10", "prio-11"}
 
 
 @pytest.mark.parametrize("cs", V.CASES, ids=[c["name"] for c in V.CASES])
