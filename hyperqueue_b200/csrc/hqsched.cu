@@ -300,50 +300,54 @@ __device__ __forceinline__ void st_release(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// min(cap, floor(n / d)) for d > 0, cap < 2^32, exact.  64-bit divisions (software routine, or FP64 reciprocals
-// with 64-bit int<->double conversions) cost several hundred cycles each and sit on the solver's sequential
-// critical path once per resource, so:
-//  (1) cap * d <= n  -> the resource does not constrain: one multiply and a compare (capacity >> demand);
-//  (2) quotient below 2^20 -> fp32 estimate from the precomputed reciprocal (the 64-bit operand is converted
-//      through its two 32-bit halves), then an exact integer fix-up of at most +-2;
-//  (3) anything else (a single worker taking more than a million tasks of one group) -> 64-bit division.
-__device__ __forceinline__ u64 div_cap(u64 n, u64 d, float rcpf, u64 cap) {
-    if (__umul64hi(d, cap) == 0 && d * cap <= n) return cap;
-    const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
-    const float qf = nf * rcpf;
-    if (qf < 1048576.0f) {
-        u64 q = (u64)__float2uint_rz(qf);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const u64 p = q * d;
-            if (p > n) --q;
-            else if (n - p >= d) ++q;
-        }
-        return q;
-    }
-    return n / d;
-}
-
 template <int RT>
 __device__ __forceinline__ bool admissible(const VarT<RT>& dv, u32 v, uint8_t blk, u64 rem_time) {
     return !((blk >> v) & 1) && (rem_time == HQS_TIME_INF || dv.min_time_ms <= rem_time);
 }
 
-// how many tasks of the variant fit into `fr` now, at most `cap` (workerload.rs:121-145 without the 1024
-// cap; `All`: feasible with >= 1 fraction (request.rs:34-36) but consumes the total (solver.rs:120-124),
-// so at most one task and only on an untouched resource)
+// How many tasks of the variant fit into `fr` now, at most `cap` (< 2^32): min over the requested resources
+// of floor(free / amount) (workerload.rs:121-145 without the 1024 cap).  `All`: feasible with >= 1 fraction
+// (request.rs:34-36) but consumes the total (solver.rs:120-124), so at most one task and only on an untouched
+// resource.
+// This sits on the solver's sequential critical path once per step, so it is STRAIGHT-LINE code: per resource
+// (independent => ILP) a multiply-compare "does cap * amount fit" test and an fp32 quotient estimate (the 64-bit
+// free amount is converted through its 32-bit halves; fp64 and 64-bit integer divisions cost hundreds of cycles)
+// with an exact two-step integer fix-up, combined by selects.  Only a binding quotient of 2^20 or more (one
+// worker taking over a million tasks of one group) falls back to a 64-bit division.
 template <int RT>
 __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[RT], const VarT<RT>& dv, u64 cap) {
     u64 cnt = cap;
+    bool big = false;
     const u32 used = dv.used_mask, allm = dv.all_mask;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-        if (!((used >> r) & 1)) continue;
-        u64 q;
-        if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
-        else if (fr[r] != HQS_AMOUNT_MAX) q = div_cap(fr[r], dv.amount[r], dv.rcpf[r], cnt);
-        else continue;
-        cnt = cnt < q ? cnt : q;
+        const bool on = (used >> r) & 1, all = (allm >> r) & 1;
+        const u64 n = fr[r], d = dv.amount[r];
+        const bool fits_cap = __umul64hi(d, cap) == 0 && d * cap <= n;
+        const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
+        const float qf = nf * dv.rcpf[r];
+        u64 q = (u64)__float2uint_rz(fminf(qf, 1048576.0f));
+        u64 p = q * d;
+        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
+        p = q * d;
+        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
+        const u64 q_all = (tot[r] != 0 && n == tot[r]) ? 1 : 0;
+        const bool unconstrained = !on || (!all && (n == HQS_AMOUNT_MAX || fits_cap));
+        big |= on && !all && !unconstrained && qf >= 1048576.0f;
+        const u64 qr = all ? q_all : q;
+        cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
+    }
+    if (big) {                                  // rare: exact 64-bit divisions
+        cnt = cap;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (!((used >> r) & 1)) continue;
+            u64 q;
+            if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
+            else if (fr[r] != HQS_AMOUNT_MAX) q = fr[r] / dv.amount[r];
+            else continue;
+            cnt = cnt < q ? cnt : q;
+        }
     }
     return cnt;
 }
@@ -374,16 +378,27 @@ __device__ void pack_body(const SolveArgs& a) {
             tot[r] = r < (int)a.R ? a.total_rw[(size_t)w * a.R + r] : 0;
         }
         const u64 rem_time = a.rem_time[w];
+        // exact u64 -> double through the 32-bit halves (one rounding, same value as a direct conversion)
+        auto to_double = [](u64 x) -> double {
+            return __dadd_rn(__dmul_rn(__uint2double_rn((u32)(x >> 32)), 4294967296.0), __uint2double_rn((u32)x));
+        };
+        // reciprocals once per worker / candidate: the per-iteration score is multiply-add only
+        double inv_tot[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            inv_tot[r] = (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX) ? __ddiv_rn(1.0, to_double(tot[r])) : 0.0;
         // my two candidates
         u32 cls[2], var[2], gi[2], quota[2], taken[2];
         bool live[2];
-        double norm[2];
+        double inv_norm[2], dvec[2][RT];
         const VarT<RT>* dv[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const u32 ci = lane + 32 * j;
             live[j] = ci < n_cand;
-            taken[j] = 0; quota[j] = 0; norm[j] = 0.0; cls[j] = var[j] = gi[j] = 0; dv[j] = &classes[0].v[0];
+            taken[j] = 0; quota[j] = 0; inv_norm[j] = 0.0; cls[j] = var[j] = gi[j] = 0; dv[j] = &classes[0].v[0];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) dvec[j][r] = 0.0;
             if (live[j]) {
                 const u32 cd = __ldcg(a.pk.cand + ci);
                 cls[j] = cd & 0xFFFFu; var[j] = (cd >> 16) & 0xFFu; gi[j] = cd >> 24;
@@ -394,19 +409,17 @@ __device__ void pack_body(const SolveArgs& a) {
                 double s2 = 0.0;
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
-                    double d = 0.0;
-                    if (((dv[j]->used_mask >> r) & 1) && tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX)
-                        d = __ddiv_rn(__ull2double_rn(dv[j]->amount[r]), __ull2double_rn(tot[r]));
-                    s2 = __dadd_rn(s2, __dmul_rn(d, d));
+                    if ((dv[j]->used_mask >> r) & 1) dvec[j][r] = __dmul_rn(to_double(dv[j]->amount[r]), inv_tot[r]);
+                    s2 = __dadd_rn(s2, __dmul_rn(dvec[j][r], dvec[j][r]));
                 }
-                norm[j] = __dsqrt_rn(s2);
+                const double nrm = __dsqrt_rn(s2);
+                inv_norm[j] = nrm > 0.0 ? __ddiv_rn(1.0, nrm) : 0.0;
             }
         }
         for (u32 it = 0; it < PACK_MAX_ITER; ++it) {
             double u[RT];
 #pragma unroll
-            for (int r = 0; r < RT; ++r)
-                u[r] = (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX) ? __ddiv_rn(__ull2double_rn(fr[r]), __ull2double_rn(tot[r])) : 0.0;
+            for (int r = 0; r < RT; ++r) u[r] = __dmul_rn(to_double(fr[r]), inv_tot[r]);
             double best_s = 0.0;
             u32 best_ci = ~0u;
 #pragma unroll
@@ -416,16 +429,11 @@ __device__ void pack_body(const SolveArgs& a) {
                 double dot = 0.0;
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
-                    double d = 0.0;
-                    if ((dv[j]->used_mask >> r) & 1) {
-                        if (fr[r] != HQS_AMOUNT_MAX && dv[j]->amount[r] > fr[r]) fits = false;
-                        if (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX)
-                            d = __ddiv_rn(__ull2double_rn(dv[j]->amount[r]), __ull2double_rn(tot[r]));
-                    }
-                    dot = __dadd_rn(dot, __dmul_rn(d, u[r]));
+                    if (((dv[j]->used_mask >> r) & 1) && fr[r] != HQS_AMOUNT_MAX && dv[j]->amount[r] > fr[r]) fits = false;
+                    dot = __dadd_rn(dot, __dmul_rn(dvec[j][r], u[r]));
                 }
                 if (!fits) continue;
-                const double s = norm[j] > 0.0 ? __ddiv_rn(dot, norm[j]) : 0.0;
+                const double s = __dmul_rn(dot, inv_norm[j]);
                 const u32 ci = lane + 32 * j;
                 if (best_ci == ~0u || s > best_s) { best_s = s; best_ci = ci; }   // j = 0 first: lower index wins ties
             }

@@ -180,20 +180,22 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int]
     taken: Dict[Tuple[int, int], int] = {}       # (w, candidate index) -> count
     for w in range(W):
         tot = t.tot[w]
-        dvec, norm = [], []
+        # reciprocals once per worker / candidate: the per-iteration score is multiply-add only
+        inv_tot = [(1.0 / float(tot[r])) if (tot[r] != 0 and tot[r] != AMOUNT_MAX) else 0.0 for r in range(R)]
+        dvec, inv_norm = [], []
         for (gi, c, v) in cands:
             d = [0.0] * R
             for r, a in t.am[c][v].items():
-                if tot[r] != 0 and tot[r] != AMOUNT_MAX:
-                    d[r] = float(a) / float(tot[r])
+                d[r] = float(a) * inv_tot[r]
             s2 = 0.0
             for r in range(R):
                 s2 = s2 + d[r] * d[r]
+            nrm = math.sqrt(s2)
             dvec.append(d)
-            norm.append(math.sqrt(s2))
+            inv_norm.append((1.0 / nrm) if nrm > 0.0 else 0.0)
         for _ in range(PACK_MAX_ITER):
             fr = t.fr[w]
-            u = [(float(fr[r]) / float(tot[r])) if (tot[r] != 0 and tot[r] != AMOUNT_MAX) else 0.0 for r in range(R)]
+            u = [float(fr[r]) * inv_tot[r] for r in range(R)]
             best, best_s = -1, 0.0
             for ci, (gi, c, v) in enumerate(cands):
                 if quota[w][gi] <= 0 or not t.admissible(w, c, v):
@@ -203,7 +205,7 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int]
                 dot = 0.0
                 for r in range(R):
                     dot = dot + dvec[ci][r] * u[r]
-                s = dot / norm[ci] if norm[ci] > 0.0 else 0.0
+                s = dot * inv_norm[ci]
                 if best < 0 or s > best_s:
                     best, best_s = ci, s
             if best < 0:
