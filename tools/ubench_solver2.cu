@@ -9,29 +9,30 @@ struct VarT { u64 amount[RT]; float rcpf[2 * RT]; u64 min_time_ms; u32 all_mask;
 struct ClassT { u32 n_variants; u32 pad; VarT v[8]; };
 struct GroupOut { u32 k, out_off, seg_lo, seg_n; };
 
-__device__ __forceinline__ u64 div_cap(u64 n, u64 d, float rcpf, u64 cap) {
-    if (__umul64hi(d, cap) == 0 && d * cap <= n) return cap;
-    const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
-    const float qf = nf * rcpf;
-    if (qf < 1048576.0f) {
-        u64 q = (u64)__float2uint_rz(qf);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) { const u64 p = q * d; if (p > n) --q; else if (n - p >= d) ++q; }
-        return q;
-    }
-    return n / d;
-}
 __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[RT], const VarT& dv, u64 cap) {
-    u64 cnt = cap; const u32 used = dv.used_mask, allm = dv.all_mask;
+    u64 cnt = cap; bool big = false;
+    const u32 used = dv.used_mask, allm = dv.all_mask;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-        if (!((used >> r) & 1)) continue;
-        u64 q;
-        if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
-        else if (fr[r] != HQS_AMOUNT_MAX) q = div_cap(fr[r], dv.amount[r], dv.rcpf[r], cnt);
-        else continue;
-        cnt = cnt < q ? cnt : q;
+        const bool on = (used >> r) & 1, all = (allm >> r) & 1;
+        const u64 n = fr[r], d = dv.amount[r];
+        const bool fits_cap = __umul64hi(d, cap) == 0 && d * cap <= n;
+        const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
+        const float qf = nf * dv.rcpf[r];
+        u64 q = (u64)__float2uint_rz(fminf(qf, 1048576.0f));
+        u64 p = q * d;
+        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
+        p = q * d;
+        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
+        const u64 q_all = (tot[r] != 0 && n == tot[r]) ? 1 : 0;
+        const bool unconstrained = !on || (!all && (n == HQS_AMOUNT_MAX || fits_cap));
+        big |= on && !all && !unconstrained && qf >= 1048576.0f;
+        const u64 qr = all ? q_all : q;
+        cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
     }
+    if (big) { cnt = cap;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { if (!((used >> r) & 1)) continue; u64 q; if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0; else if (fr[r] != HQS_AMOUNT_MAX) q = fr[r] / dv.amount[r]; else continue; cnt = cnt < q ? cnt : q; } }
     return cnt;
 }
 
@@ -60,10 +61,10 @@ __global__ void k(const ClassT* g_classes, const uint2* g_glist, int n_list, u64
         const u32 seg_lo = seg_base;
         const VarT& dv = classes[c].v[0];
         u64 cnt = 0;
-        if (MODE >= 1) cnt = fit_count(fr, tot, dv, remaining); else cnt = (tid == (u32)(e & 255)) ? remaining : 0;
+        if (MODE >= 1) cnt = fit_count(fr, tot, dv, remaining); else cnt = (tid >= (u32)(e & 127)) ? remaining : 0;
         const bool can1 = cnt != 0, can_all = cnt >= remaining;
         u32 take = 0, exc_cnt = 0, seg_rank = 0, n_takers = 0, handed = 0;
-        if (MODE >= 2) {
+        if (MODE >= 0) {
             u64* fb = s_f + 32 * (parity & 1); parity++;
             const u32 has = __ballot_sync(0xffffffffu, can1);
             const u32 first = has ? (u32)(__ffs(has) - 1) : 0u;
@@ -129,7 +130,7 @@ int main() {
     cudaMalloc(&d_cls, sizeof h_cls); cudaMalloc(&d_gl, sizeof h_gl); cudaMalloc(&d_out, 1024 * 8); cudaMalloc(&d_cyc, 8); cudaMalloc(&d_go, 256 * 16);
     cudaMemcpy(d_cls, h_cls, sizeof h_cls, cudaMemcpyHostToDevice); cudaMemcpy(d_gl, h_gl, sizeof h_gl, cudaMemcpyHostToDevice);
     const size_t smem = 16 * sizeof(ClassT) + 256 * 8 + 2 * 4096 * 4 + 256 * 16;
-    const char* names[] = {"loop + smem group/class reads only", "+ fit_count", "+ exchange, fast path, scan", "  (scan forced on every step)", "+ segments, take", "+ group record"};
+    const char* names[] = {"exchange + fast path (trivial count)", "fit_count + exchange + fast path", "same", "  scan forced on every step", "+ segments, take (loop-carried free)", "+ group record"};
 #define RUN(M) { cudaFuncSetAttribute(k<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); for (int rep = 0; rep < 2; ++rep) { k<M><<<1, 256, smem>>>(d_cls, d_gl, n_list, d_out, d_cyc, d_go); cudaDeviceSynchronize(); } long long c; cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost); printf("%-45s %8.1f cycles/group\n", names[M], (double)c / n_list); }
     RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
