@@ -53,7 +53,8 @@ class hqs_worker(C.Structure):
 class hqs_stats(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_levels", C.c_uint32), ("n_assigned", C.c_uint32),
                 ("n_segments", C.c_uint32), ("kernel_launches", C.c_uint64), ("ticks", C.c_uint64),
-                ("n_handles", C.c_uint32), ("coarsened", C.c_uint32)]
+                ("n_handles", C.c_uint32), ("coarsened", C.c_uint32),
+                ("narrow_amounts", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 worker_dtype = np.dtype([("worker_id", "<u4"), ("flags", "<u4"), ("remaining_time_ms", "<u8"),

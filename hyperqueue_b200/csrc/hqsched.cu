@@ -33,6 +33,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <numeric>
 #include <vector>
 
 namespace {
@@ -228,20 +229,29 @@ constexpr u32 PACK_CHUNK_DIV = 8;
 constexpr u32 PHASE_WAIT = 0, PHASE_PACK = 1, PHASE_EXIT = 2;
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: a stuck grid must not hang the GPU
 
-template <int RT>
+// Amounts come in two widths.  u64: the ABI's fixed-point fractions as they are.  u32 ("narrow"): the same
+// amounts divided by the per-resource gcd of all requested amounts — fit counts are unchanged by that
+// (floor(n / d) == floor(floor(n / g) / (d / g)) when g divides d), the quotient estimate needs one int->float
+// conversion and one fix-up instead of a 64-bit sequence, and the solver's sequential critical path shrinks
+// accordingly.  The narrow path is taken when every scaled amount of the tick is below 2^31.
+template <int RT, typename AT = u64>
 struct VarT {
-    u64 amount[RT];
-    float rcpf[2 * RT];  // [0, RT): fp32 1.0 / amount (0 where unused) for the quotient estimate; rest: padding
+    AT amount[RT];
+    float rcpf[sizeof(AT) == 8 ? 2 * RT : RT];  // [0, RT): fp32 1.0 / amount (0 where unused); rest: padding
     u64 min_time_ms;
     u32 all_mask;
     u32 used_mask;
 };
-template <int RT>
+template <int RT, typename AT = u64>
 struct ClassT {
     u32 n_variants;
     u32 pad;
-    VarT<RT> v[HQS_MAX_VARIANTS];
+    VarT<RT, AT> v[HQS_MAX_VARIANTS];
 };
+template <typename AT> struct AmountMax;
+template <> struct AmountMax<u64> { static constexpr u64 value = HQS_AMOUNT_MAX; };
+template <> struct AmountMax<u32> { static constexpr u32 value = 0xFFFFFFFFu; };
+constexpr u64 NARROW_LIMIT = 0x7FFFFFFFull;      // scaled amounts of the narrow path stay below 2^31
 
 struct SolveSync {
     u32 phase;
@@ -264,9 +274,11 @@ struct SolveArgs {
     const u32* order;        // [Q] class ids in processing order inside one priority level
     const uint8_t* vorder;   // [Q][HQS_MAX_VARIANTS] variant ids in first-fit order
     const uint8_t* blocked;  // [W][Q] bytes (bit v) or nullptr
-    const void* classes;     // ClassT<RT>[Q]
+    const void* classes;     // ClassT<RT, AT>[Q] of the solver's width
+    const void* classes64;   // ClassT<RT, u64>[Q] (the pack warps work on exact amounts)
+    u64 gscale[HQS_MAX_RESOURCES];   // narrow path: amount = scaled amount * gscale[r] (+ a per-worker remainder)
     u32 W, Q, L, R, G;
-    u32 classes_bytes;       // Q * sizeof(ClassT<RT>)
+    u32 classes_bytes;       // Q * sizeof(ClassT<RT, AT>)
     u32 smem_classes;        // 1: stage the class table in shared memory
     u32 smem_glist_cap;      // group-list entries staged in shared memory
     u32 smem_vorder;         // 1: stage vorder[] in shared memory
@@ -300,22 +312,22 @@ __device__ __forceinline__ void st_release(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int RT>
-__device__ __forceinline__ bool admissible(const VarT<RT>& dv, u32 v, uint8_t blk, u64 rem_time) {
+template <int RT, typename AT>
+__device__ __forceinline__ bool admissible(const VarT<RT, AT>& dv, u32 v, uint8_t blk, u64 rem_time) {
     return !((blk >> v) & 1) && (rem_time == HQS_TIME_INF || dv.min_time_ms <= rem_time);
 }
 
 // How many tasks of the variant fit into `fr` now, at most `cap` (< 2^32): min over the requested resources
 // of floor(free / amount) (workerload.rs:121-145 without the 1024 cap).  `All`: feasible with >= 1 fraction
 // (request.rs:34-36) but consumes the total (solver.rs:120-124), so at most one task and only on an untouched
-// resource.
+// resource: bit r of `allok` says "total[r] != 0 and the parts of free/total the scaling dropped are equal".
 // This sits on the solver's sequential critical path once per step, so it is STRAIGHT-LINE code: per resource
-// (independent => ILP) a multiply-compare "does cap * amount fit" test and an fp32 quotient estimate (the 64-bit
-// free amount is converted through its 32-bit halves; fp64 and 64-bit integer divisions cost hundreds of cycles)
-// with an exact two-step integer fix-up, combined by selects.  Only a binding quotient of 2^20 or more (one
-// worker taking over a million tasks of one group) falls back to a 64-bit division.
+// (independent => ILP) a multiply-compare "does cap * amount fit" test and an fp32 quotient estimate with an
+// exact integer fix-up, combined by selects.  Only a binding quotient of 2^20 or more (one worker taking over
+// a million tasks of one group) falls back to an integer division.
 template <int RT>
-__device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[RT], const VarT<RT>& dv, u64 cap) {
+__device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[RT], u32 allok, const VarT<RT, u64>& dv,
+                                         u64 cap) {
     u64 cnt = cap;
     bool big = false;
     const u32 used = dv.used_mask, allm = dv.all_mask;
@@ -324,6 +336,7 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
         const bool on = (used >> r) & 1, all = (allm >> r) & 1;
         const u64 n = fr[r], d = dv.amount[r];
         const bool fits_cap = __umul64hi(d, cap) == 0 && d * cap <= n;
+        // the 64-bit free amount is converted through its 32-bit halves (fp64 and 64-bit divisions cost hundreds of cycles)
         const float nf = __fmaf_rn(__uint2float_rn((u32)(n >> 32)), 4294967296.0f, __uint2float_rn((u32)n));
         const float qf = nf * dv.rcpf[r];
         u64 q = (u64)__float2uint_rz(fminf(qf, 1048576.0f));
@@ -331,7 +344,7 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
         q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
         p = q * d;
         q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
-        const u64 q_all = (tot[r] != 0 && n == tot[r]) ? 1 : 0;
+        const u64 q_all = (((allok >> r) & 1) && n == tot[r]) ? 1 : 0;
         const bool unconstrained = !on || (!all && (n == HQS_AMOUNT_MAX || fits_cap));
         big |= on && !all && !unconstrained && qf >= 1048576.0f;
         const u64 qr = all ? q_all : q;
@@ -343,7 +356,7 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
         for (int r = 0; r < RT; ++r) {
             if (!((used >> r) & 1)) continue;
             u64 q;
-            if ((allm >> r) & 1) q = (tot[r] != 0 && fr[r] == tot[r]) ? 1 : 0;
+            if ((allm >> r) & 1) q = (((allok >> r) & 1) && fr[r] == tot[r]) ? 1 : 0;
             else if (fr[r] != HQS_AMOUNT_MAX) q = fr[r] / dv.amount[r];
             else continue;
             cnt = cnt < q ? cnt : q;
@@ -352,20 +365,59 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
     return cnt;
 }
 
+// Narrow amounts (< 2^31): one conversion, one multiply and a single +-1 fix-up per resource — the fp32 estimate
+// of a quotient below 2^20 is off by less than one (relative error < 2^-22).
 template <int RT>
-__device__ __forceinline__ void take_from(u64 (&fr)[RT], const VarT<RT>& dv, u64 k) {
+__device__ __forceinline__ u64 fit_count(const u32 (&fr)[RT], const u32 (&tot)[RT], u32 allok, const VarT<RT, u32>& dv,
+                                         u64 cap64) {
+    const u32 cap = (u32)cap64;
+    u32 cnt = cap;
+    bool big = false;
+    const u32 used = dv.used_mask, allm = dv.all_mask;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const bool on = (used >> r) & 1, all = (allm >> r) & 1;
+        const u32 n = fr[r], d = dv.amount[r];
+        const bool fits_cap = (u64)d * cap <= (u64)n;
+        const float qf = __uint2float_rn(n) * dv.rcpf[r];
+        u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
+        const u32 p = q * d;
+        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
+        const u32 q_all = (((allok >> r) & 1) && n == tot[r]) ? 1u : 0u;
+        const bool unconstrained = !on || (!all && (n == 0xFFFFFFFFu || fits_cap));
+        big |= on && !all && !unconstrained && qf >= 1048576.0f;
+        const u32 qr = all ? q_all : q;
+        cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
+    }
+    if (big) {                                  // rare: exact divisions
+        cnt = cap;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (!((used >> r) & 1)) continue;
+            u32 q;
+            if ((allm >> r) & 1) q = (((allok >> r) & 1) && fr[r] == tot[r]) ? 1u : 0u;
+            else if (fr[r] != 0xFFFFFFFFu) q = fr[r] / dv.amount[r];
+            else continue;
+            cnt = cnt < q ? cnt : q;
+        }
+    }
+    return cnt;
+}
+
+template <int RT, typename AT>
+__device__ __forceinline__ void take_from(AT (&fr)[RT], const VarT<RT, AT>& dv, u64 k) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
         if (!((dv.used_mask >> r) & 1)) continue;
         if ((dv.all_mask >> r) & 1) fr[r] = 0;                               // workerload.rs:162
-        else if (fr[r] != HQS_AMOUNT_MAX) fr[r] -= k * dv.amount[r];
+        else if (fr[r] != AmountMax<AT>::value) fr[r] -= (AT)k * dv.amount[r];
     }
 }
 
 // ---- pack: one warp fills one worker (specification: tests/greedy_model.py::_pack_level step b) ----
 template <int RT>
 __device__ void pack_body(const SolveArgs& a) {
-    const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
+    const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes64);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 n_pack_ctas = gridDim.x - 1;
     const u32 n_cand = __ldcg(a.pk.meta);
@@ -377,6 +429,9 @@ __device__ void pack_body(const SolveArgs& a) {
             fr[r] = r < (int)a.R ? __ldcg(a.pk.fr + (size_t)w * a.R + r) : 0;
             tot[r] = r < (int)a.R ? a.total_rw[(size_t)w * a.R + r] : 0;
         }
+        u32 allok = 0;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) allok |= tot[r] != 0 ? (1u << r) : 0u;
         const u64 rem_time = a.rem_time[w];
         // exact u64 -> double through the 32-bit halves (one rounding, same value as a direct conversion)
         auto to_double = [](u64 x) -> double {
@@ -450,7 +505,7 @@ __device__ void pack_body(const SolveArgs& a) {
             const VarT<RT>* mydv = oj ? dv[1] : dv[0];
             if (lane == owner) {
                 const u32 q = oj ? quota[1] : quota[0];
-                const u64 f = fit_count<RT>(fr, tot, *mydv, q);
+                const u64 f = fit_count<RT>(fr, tot, allok, *mydv, q);
                 const u32 chunk = q / PACK_CHUNK_DIV > 1 ? q / PACK_CHUNK_DIV : 1;
                 k = (u32)(f < chunk ? f : chunk);
                 if (oj) taken[1] += k; else taken[0] += k;
@@ -460,7 +515,7 @@ __device__ void pack_body(const SolveArgs& a) {
             ggi = __shfl_sync(0xffffffffu, ggi, owner);
             // every lane applies the owner's amounts to its copy of the free vector
             const VarT<RT>* odv = (const VarT<RT>*)__shfl_sync(0xffffffffu, (unsigned long long)mydv, owner);
-            take_from<RT>(fr, *odv, k);
+            take_from<RT, u64>(fr, *odv, k);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (gi[j] == ggi && (lane + 32 * j) < n_cand) quota[j] = quota[j] >= k ? quota[j] - k : 0;
@@ -521,8 +576,12 @@ __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u
     return o;
 }
 
-template <int RT, bool SMALL>
+template <int RT, bool SMALL, typename AT>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
+    constexpr bool NARROW = sizeof(AT) == 4;
+    constexpr AT AMAX = AmountMax<AT>::value;
+    using Var = VarT<RT, AT>;
+    using Cls = ClassT<RT, AT>;
     __shared__ u64 s_x[64], s_f[64];
     __shared__ u64 s_red[2 * 32 * (2 * RT + 1)];
     __shared__ u64 s_totmax[RT];
@@ -536,21 +595,21 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
 
     // ---- class table and variant order: in shared memory when they fit (SMALL: the pointers are then
     //      provably shared, so the sequential critical path uses LDS, not generic loads), else global
-    const ClassT<RT>* classes;
+    const Cls* classes;
     const uint8_t* vorder;
     unsigned char* sp = smem_dyn;
     if constexpr (SMALL) {
         const uint4* src = reinterpret_cast<const uint4*>(a.classes);
         uint4* dst = reinterpret_cast<uint4*>(smem_dyn);
         for (u32 i = tid; i < a.classes_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        classes = reinterpret_cast<const ClassT<RT>*>(smem_dyn);
+        classes = reinterpret_cast<const Cls*>(smem_dyn);
         sp += (a.classes_bytes + 15u) & ~15u;
         uint8_t* sv = sp;
         for (u32 i = tid; i < a.Q * HQS_MAX_VARIANTS; i += blockDim.x) sv[i] = a.vorder[i];
         vorder = sv;
         sp += (a.Q * HQS_MAX_VARIANTS + 15u) & ~15u;
     } else {
-        classes = reinterpret_cast<const ClassT<RT>*>(a.classes);
+        classes = reinterpret_cast<const Cls*>(a.classes);
         vorder = a.vorder;
     }
     uint2* s_glist = reinterpret_cast<uint2*>(sp);
@@ -570,19 +629,44 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
 
     const long long t_start = clock64();
     long long t_sat = 0, t_groups = 0;
-    u64 fr[RT], tot[RT];
+    // worker state in registers.  Narrow path: fr/tot hold floor(amount / gscale[r]), `rem` what the division
+    // dropped (exact amount = fr * gscale + rem; requests are multiples of gscale, so rem only changes when an
+    // `All` request empties the resource).
+    AT fr[RT], tot[RT];
+    u64 rem[NARROW ? RT : 1];
+    u32 allok = 0;      // bit r: total != 0 and free/total agree in the dropped part (-> `All` needs fr == tot)
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-        fr[r] = (has_worker && r < (int)a.R) ? a.free_rw[(size_t)tid * a.R + r] : 0;
-        tot[r] = (has_worker && r < (int)a.R) ? a.total_rw[(size_t)tid * a.R + r] : 0;
+        const u64 n = (has_worker && r < (int)a.R) ? a.free_rw[(size_t)tid * a.R + r] : 0;
+        const u64 t = (has_worker && r < (int)a.R) ? a.total_rw[(size_t)tid * a.R + r] : 0;
+        if constexpr (NARROW) {
+            const u64 g = a.gscale[r];
+            const u64 nq = g == 1 ? n : n / g, tq = g == 1 ? t : t / g;
+            fr[r] = n == HQS_AMOUNT_MAX ? AMAX : (AT)nq;
+            tot[r] = t == HQS_AMOUNT_MAX ? AMAX : (AT)tq;
+            rem[r] = n == HQS_AMOUNT_MAX ? 0 : n - nq * g;
+            const u64 trem = t == HQS_AMOUNT_MAX ? 0 : t - tq * g;
+            allok |= (t != 0 && rem[r] == trem) ? (1u << r) : 0u;
+        } else {
+            fr[r] = n; tot[r] = t;
+            allok |= t != 0 ? (1u << r) : 0u;
+        }
     }
+    auto exact_free = [&](int r) -> u64 {
+        if constexpr (NARROW) return fr[r] == AMAX ? HQS_AMOUNT_MAX : (u64)fr[r] * a.gscale[r] + rem[r];
+        else return fr[r];
+    };
+    auto exact_amount = [&](const Var& dv, int r) -> u64 {
+        if constexpr (NARROW) return (u64)dv.amount[r] * a.gscale[r];
+        else return dv.amount[r];
+    };
     const u64 rem_time = has_worker ? a.rem_time[tid] : 0;
     // per-resource maximum of the worker totals (a class no worker is big enough for is not demand)
     {
         u64 m[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
-            m[r] = tot[r];
+            m[r] = (u64)tot[r];
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) { const u64 y = __shfl_xor_sync(0xffffffffu, m[r], d); m[r] = y > m[r] ? y : m[r]; }
         }
@@ -673,7 +757,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             constexpr int NV = 2 * RT + 1;
             u64 val[NV];
 #pragma unroll
-            for (int r = 0; r < RT; ++r) { val[r] = has_worker ? fr[r] : 0; val[RT + r] = 0; }
+            for (int r = 0; r < RT; ++r) { val[r] = has_worker ? exact_free(r) : 0; val[RT + r] = 0; }
             val[2 * RT] = 0;
             if (tid < ng) {
                 const uint2 ge = GL(li + tid);
@@ -682,14 +766,15 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 u64 flag = 0;
                 for (u32 v = 0; v < nvv; ++v) flag |= classes[c].v[v].all_mask ? (1ull << 32) : 0ull;
                 val[2 * RT] = nvv | flag;                                  // low: candidates, bit 32+: has `All`
-                const VarT<RT>& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
+                const Var& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
                 bool servable = true;
 #pragma unroll
-                for (int r = 0; r < RT; ++r) servable &= dv.amount[r] <= s_totmax[r];
+                for (int r = 0; r < RT; ++r) servable &= (u64)dv.amount[r] <= s_totmax[r];
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
-                    const u64 hi = __umul64hi(dv.amount[r], (u64)ge.y);
-                    val[RT + r] = !servable ? 0 : (hi ? HQS_AMOUNT_MAX : dv.amount[r] * (u64)ge.y);
+                    const u64 amt = exact_amount(dv, r);
+                    const u64 hi = __umul64hi(amt, (u64)ge.y);
+                    val[RT + r] = !servable ? 0 : (hi ? HQS_AMOUNT_MAX : amt * (u64)ge.y);
                 }
             }
 #pragma unroll
@@ -734,9 +819,9 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                         u64 cn = 0;
                         if (has_worker)
                             for (u32 v = 0; v < classes[c].n_variants; ++v) {
-                                const VarT<RT>& dv = classes[c].v[v];
+                                const Var& dv = classes[c].v[v];
                                 if (!admissible(dv, v, blk, rem_time)) continue;
-                                const u64 f = fit_count<RT>(fr, tot, dv, n);
+                                const u64 f = fit_count<RT>(fr, tot, allok, dv, n);
                                 cn = f > cn ? f : cn;
                             }
                         u64 x = cn;
@@ -757,7 +842,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (has_worker) {
 #pragma unroll
                         for (int r = 0; r < RT; ++r)
-                            if (r < (int)a.R) a.pk.fr[(size_t)tid * a.R + r] = fr[r];
+                            if (r < (int)a.R) a.pk.fr[(size_t)tid * a.R + r] = exact_free(r);
                     }
                     if (tid == 0) {
                         u32 ci = 0;
@@ -786,7 +871,15 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     if (has_worker) {
 #pragma unroll
                         for (int r = 0; r < RT; ++r)
-                            if (r < (int)a.R) fr[r] = __ldcg(a.pk.fr + (size_t)tid * a.R + r);
+                            if (r < (int)a.R) {
+                                const u64 x = __ldcg(a.pk.fr + (size_t)tid * a.R + r);
+                                if constexpr (NARROW) {
+                                    const u64 g = a.gscale[r];
+                                    fr[r] = x == HQS_AMOUNT_MAX ? AMAX : (AT)(g == 1 ? x - rem[r] : (x - rem[r]) / g);
+                                } else {
+                                    fr[r] = x;
+                                }
+                            }
                     }
                     packed = true;
                     level_packed = !sync_timeout;
@@ -817,7 +910,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     const u64 cnt = has_worker ? __ldcg(a.pk.taken + (size_t)tid * PACK_MAX_CAND + cand_base + v) : 0;
                     u32 seg_rank;
                     ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
-                    const VarT<RT>& dv = classes[c].v[v];
+                    const Var& dv = classes[c].v[v];
                     if (o.take) {
                         const u32 si = seg_base + seg_rank;
                         if (si < SEG_CAP) {
@@ -829,7 +922,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                         const u64 ex = cnt - o.take;
 #pragma unroll
                         for (int r = 0; r < RT; ++r)
-                            if (((dv.used_mask >> r) & 1) && fr[r] != HQS_AMOUNT_MAX) fr[r] += ex * dv.amount[r];
+                            if (((dv.used_mask >> r) & 1) && fr[r] != AMAX) fr[r] += (AT)ex * dv.amount[r];
                     }
                     const u32 n_takers = (u32)__syncthreads_count(o.take != 0);
                     remaining -= (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
@@ -840,12 +933,12 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             }
             for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
                 const u32 v = vorder[c * HQS_MAX_VARIANTS + vi];
-                const VarT<RT>& dv = classes[c].v[v];
+                const Var& dv = classes[c].v[v];
                 FLUSH_SEGMENTS_IF_FULL();
                 // exact count once (reciprocal division, capped at `remaining`): can1 = cnt > 0, and the
                 // first worker takes everything iff its cnt == remaining
                 u64 cnt = 0;
-                if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, dv, remaining);
+                if (has_worker && admissible(dv, v, blk, rem_time)) cnt = fit_count<RT>(fr, tot, allok, dv, remaining);
                 const bool can1 = cnt != 0, can_all = cnt >= remaining;
                 u32 take = 0, exc_cnt = 0, seg_rank = 0, n_takers = 0, handed = 0;
                 {
@@ -878,7 +971,17 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                         s_segc[si - seg_flushed] = (n_all - remaining) + exc_cnt + take;
                         s_segw[si - seg_flushed] = tid | (v << 16);
                     }
-                    take_from<RT>(fr, dv, take);
+                    take_from<RT, AT>(fr, dv, take);
+                    if constexpr (NARROW) {
+                        // `All` consumed the whole resource: the exact free amount is 0, remainder included
+                        const u32 z = dv.all_mask & dv.used_mask;
+                        if (z) {
+#pragma unroll
+                            for (int r = 0; r < RT; ++r)
+                                if ((z >> r) & 1) rem[r] = 0;
+                            allok &= ~z;
+                        }
+                    }
                 }
                 remaining -= handed;
                 seg_base += n_takers;
@@ -911,14 +1014,14 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 bool can = false;
                 if (has_worker)
                     for (u32 v = 0; v < classes[c].n_variants && !can; ++v) {
-                        const VarT<RT>& dv = classes[c].v[v];
+                        const Var& dv = classes[c].v[v];
                         if (!admissible(dv, v, blk, rem_time)) continue;
                         bool ok = true;
 #pragma unroll
                         for (int r = 0; r < RT; ++r) {
                             if (!((dv.used_mask >> r) & 1)) continue;
-                            if ((dv.all_mask >> r) & 1) ok &= tot[r] != 0 && fr[r] == tot[r];
-                            else if (fr[r] != HQS_AMOUNT_MAX) ok &= dv.amount[r] <= fr[r];
+                            if ((dv.all_mask >> r) & 1) ok &= ((allok >> r) & 1) && fr[r] == tot[r];
+                            else if (fr[r] != AMAX) ok &= dv.amount[r] <= fr[r];
                         }
                         can = ok;
                     }
@@ -946,7 +1049,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     if (has_worker) {
 #pragma unroll
         for (int r = 0; r < RT; ++r)
-            if (r < (int)a.R) a.free_after[(size_t)tid * a.R + r] = fr[r];
+            if (r < (int)a.R) a.free_after[(size_t)tid * a.R + r] = exact_free(r);
     }
     if (tid == 0) {
         a.hdr->n_assigned = out_base;
@@ -964,11 +1067,11 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
 #undef FLUSH_SEGMENTS_IF_FULL
 }
 
-template <int RT, int MAXT, bool SMALL>
+template <int RT, int MAXT, bool SMALL, typename AT>
 __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     if (blockIdx.x == 0) {
-        solve_body<RT, SMALL>(a, smem_dyn);
+        solve_body<RT, SMALL, AT>(a, smem_dyn);
         return;
     }
     // ---- exclusive scan over chunks: one warp per group column, 32 chunk rows per step
@@ -991,6 +1094,7 @@ __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
             }
         }
     }
+    if (!a.pack_enabled) return;            // nothing to stand by for
     // ---- wait for CTA 0's decision
     __shared__ u32 s_cmd;
     if (threadIdx.x == 0) {
@@ -1186,8 +1290,16 @@ struct hqs_ctx {
     // classes
     u32 Q = 0;
     std::vector<hqs_class> classes;
-    unsigned char* d_classes = nullptr;   // ClassT<RT>[Q]
+    unsigned char* d_classes = nullptr;   // ClassT<RT, u64>[Q]
     u32 d_classes_cap = 0;                // bytes
+    unsigned char* d_classes32 = nullptr; // ClassT<RT, u32>[Q]: amounts / gscale[r] (valid when narrow_classes)
+    u32 d_classes32_cap = 0;
+    u32 class_bytes32 = 0;                // sizeof(ClassT<RT, u32>)
+    u64 gscale[HQS_MAX_RESOURCES] = {};   // per-resource gcd of every requested amount (1 where nothing is requested)
+    u64 narrow_limit[HQS_MAX_RESOURCES] = {};   // largest worker amount the narrow path can hold: gscale * (2^31 - 1)
+    bool narrow_classes = false;          // every scaled class amount < 2^31
+    bool tick_narrow = false;             // this tick runs the narrow solver
+    bool force_wide = false;              // hqs_create flag bit 1: always the 64-bit solver (tests)
     u32 RT = 4;                           // resource slots of the device class layout (4, 8 or 16)
     u32 class_bytes = 0;                  // sizeof(ClassT<RT>)
     // priority levels (descending)
@@ -1515,6 +1627,20 @@ int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64*
     unsigned char* h = ctx->h_tickin;
     memcpy(h + lay.off_free, free_rw, (size_t)W * R * 8);
     memcpy(h + lay.off_total, total_rw, (size_t)W * R * 8);
+    // narrow solver: every worker amount of this tick must fit 31 bits after the per-resource scaling
+    static const bool force_wide = getenv("HQS_DEBUG_WIDE") != nullptr;
+    bool narrow = ctx->narrow_classes && !force_wide && !ctx->force_wide;
+    if (narrow) {
+        u64 over = 0;
+        for (u32 w = 0; w < W; ++w)
+            for (u32 r = 0; r < R; ++r) {
+                const u64 f = free_rw[(size_t)w * R + r], t = total_rw[(size_t)w * R + r], lim = ctx->narrow_limit[r];
+                over |= (u64)(f != HQS_AMOUNT_MAX && f > lim) | (u64)(t != HQS_AMOUNT_MAX && t > lim);
+            }
+        narrow = over == 0;
+    }
+    ctx->tick_narrow = narrow;
+    ctx->stats.narrow_amounts = narrow ? 1 : 0;
     u64* rem = reinterpret_cast<u64*>(h + lay.off_rem);
     for (u32 w = 0; w < W; ++w) rem[w] = workers[w].remaining_time_ms;
     tick_orders(ctx, W, free_rw, total_rw, reinterpret_cast<u32*>(h + lay.off_order), h + lay.off_vorder);
@@ -1525,6 +1651,24 @@ int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64*
     CU(cudaMemcpyAsync(ctx->d_tickin, h, lay.bytes, cudaMemcpyHostToDevice, ctx->stream));
     *lay_out = lay;
     return HQS_OK;
+}
+
+// maxima of two u32 arrays, eight independent accumulators each (the compiler turns them into vector max)
+void max_of_u32_pair(const u32* a, const u32* b, u32 n, u32* max_a, u32* max_b) {
+    u32 ma[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (u32 j = 0; j < 8; ++j) {
+            ma[j] = a[i + j] > ma[j] ? a[i + j] : ma[j];
+            mb[j] = b[i + j] > mb[j] ? b[i + j] : mb[j];
+        }
+    for (; i < n; ++i) {
+        ma[0] = a[i] > ma[0] ? a[i] : ma[0];
+        mb[0] = b[i] > mb[0] ? b[i] : mb[0];
+    }
+    for (u32 j = 1; j < 8; ++j) { ma[0] = ma[j] > ma[0] ? ma[j] : ma[0]; mb[0] = mb[j] > mb[0] ? mb[j] : mb[0]; }
+    *max_a = ma[0];
+    *max_b = mb[0];
 }
 
 int validate_workers(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw) {
@@ -1557,9 +1701,12 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.order = reinterpret_cast<const u32*>(ctx->d_tickin + lay.off_order);
     a.vorder = ctx->d_tickin + lay.off_vorder;
     a.blocked = blocked ? ctx->d_tickin + lay.off_blocked : nullptr;
-    a.classes = ctx->d_classes;
+    const bool narrow = ctx->tick_narrow;
+    a.classes = narrow ? ctx->d_classes32 : ctx->d_classes;
+    a.classes64 = ctx->d_classes;
+    for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) a.gscale[r] = ctx->gscale[r] ? ctx->gscale[r] : 1;
     a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
-    a.classes_bytes = ctx->Q * ctx->class_bytes;
+    a.classes_bytes = ctx->Q * (narrow ? ctx->class_bytes32 : ctx->class_bytes);
     a.total_local = ctx->d_total;
     a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
     a.before = d_before;
@@ -1594,9 +1741,11 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     void* kargs[] = {&a};
     const bool small = a.smem_classes != 0;
     const void* fn;
-#define HQS_PICK(MT, SM) (ctx->RT == 4 ? (const void*)solve_k<4, MT, SM> : ctx->RT == 8 ? (const void*)solve_k<8, MT, SM> : (const void*)solve_k<16, MT, SM>)
-    if (threads <= 256) fn = small ? HQS_PICK(256, true) : HQS_PICK(256, false);
-    else fn = small ? HQS_PICK(1024, true) : HQS_PICK(1024, false);
+#define HQS_PICK(MT, SM, AT) (ctx->RT == 4 ? (const void*)solve_k<4, MT, SM, AT> : ctx->RT == 8 ? (const void*)solve_k<8, MT, SM, AT> : (const void*)solve_k<16, MT, SM, AT>)
+#define HQS_PICK2(MT, SM) (narrow ? HQS_PICK(MT, SM, u32) : HQS_PICK(MT, SM, u64))
+    if (threads <= 256) fn = small ? HQS_PICK2(256, true) : HQS_PICK2(256, false);
+    else fn = small ? HQS_PICK2(1024, true) : HQS_PICK2(1024, false);
+#undef HQS_PICK2
 #undef HQS_PICK
     static const bool no_coop = getenv("HQS_DEBUG_NO_COOP") != nullptr;   // profiling aid: ncu skips cooperative launches
     if (no_coop) CU(cudaLaunchKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
@@ -1645,7 +1794,9 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     ctx->R = n_resources;
     ctx->RT = n_resources <= 4 ? 4 : n_resources <= 8 ? 8 : 16;
     ctx->class_bytes = ctx->RT == 4 ? sizeof(ClassT<4>) : ctx->RT == 8 ? sizeof(ClassT<8>) : sizeof(ClassT<16>);
+    ctx->class_bytes32 = ctx->RT == 4 ? sizeof(ClassT<4, u32>) : ctx->RT == 8 ? sizeof(ClassT<8, u32>) : sizeof(ClassT<16, u32>);
     ctx->pack = !(flags & 1u);
+    ctx->force_wide = (flags & 2u) != 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     int sms = 0;
@@ -1654,18 +1805,16 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<8, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_k<16, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    {
+        const void* fns[] = {
+#define HQS_ALL(RTV, AT) (const void*)solve_k<RTV, 256, true, AT>, (const void*)solve_k<RTV, 256, false, AT>, \
+                         (const void*)solve_k<RTV, 1024, true, AT>, (const void*)solve_k<RTV, 1024, false, AT>
+            HQS_ALL(4, u64), HQS_ALL(8, u64), HQS_ALL(16, u64), HQS_ALL(4, u32), HQS_ALL(8, u32), HQS_ALL(16, u32)
+#undef HQS_ALL
+        };
+        for (const void* f : fns)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete ctx;
@@ -1680,7 +1829,7 @@ void hqs_destroy(hqs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* dev_ptrs[] = {ctx->d_classes, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
+    void* dev_ptrs[] = {ctx->d_classes, ctx->d_classes32, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
                         ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
                         ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_glist, ctx->d_seg_cum,
                         ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
@@ -1742,6 +1891,54 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
         CU(cudaMalloc(&ctx->d_classes, ctx->d_classes_cap));
     }
     CU(cudaMemcpyAsync(ctx->d_classes, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // narrow copy: amounts divided by the per-resource gcd of everything requested
+    u64 gs[HQS_MAX_RESOURCES];
+    for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) gs[r] = 0;
+    for (u32 c = 0; c < n_classes; ++c)
+        for (u32 v = 0; v < classes[c].n_variants; ++v)
+            for (u32 r = 0; r < ctx->R; ++r)
+                if (!((classes[c].variants[v].all_mask >> r) & 1) && classes[c].variants[v].amount[r])
+                    gs[r] = std::gcd(gs[r], (u64)classes[c].variants[v].amount[r]);
+    bool narrow_ok = true;
+    const size_t var_bytes32 = (size_t)RT * 8 + 16, cls_bytes32 = ctx->class_bytes32;
+    std::vector<unsigned char> blob32((size_t)n_classes * cls_bytes32, 0);
+    for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) {
+        if (gs[r] == 0) gs[r] = 1;
+        ctx->gscale[r] = gs[r];
+        ctx->narrow_limit[r] = gs[r] > HQS_AMOUNT_MAX / NARROW_LIMIT ? HQS_AMOUNT_MAX - 1 : gs[r] * NARROW_LIMIT;
+    }
+    for (u32 c = 0; c < n_classes && narrow_ok; ++c) {
+        const hqs_class& sc = classes[c];
+        unsigned char* cb = blob32.data() + (size_t)c * cls_bytes32;
+        memcpy(cb, &sc.n_variants, 4);
+        for (u32 v = 0; v < sc.n_variants; ++v) {
+            unsigned char* vb = cb + 8 + (size_t)v * var_bytes32;
+            u32* amount = reinterpret_cast<u32*>(vb);
+            float* rcp = reinterpret_cast<float*>(vb + (size_t)RT * 4);
+            u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 8);
+            u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 8 + 8);
+            u32 used = 0;
+            for (u32 r = 0; r < ctx->R; ++r) {
+                const bool all = (sc.variants[v].all_mask >> r) & 1;
+                const u64 amt = all ? 0 : sc.variants[v].amount[r] / gs[r];
+                if (amt > NARROW_LIMIT) narrow_ok = false;
+                amount[r] = (u32)amt;
+                rcp[r] = amt ? 1.0f / (float)(u32)amt : 0.0f;
+                if (all || sc.variants[v].amount[r]) used |= 1u << r;
+            }
+            *min_time = sc.variants[v].min_time_ms;
+            masks[0] = sc.variants[v].all_mask & ((1u << ctx->R) - 1);
+            masks[1] = used;
+        }
+    }
+    ctx->narrow_classes = narrow_ok;
+    if (blob32.size() > ctx->d_classes32_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_classes32) CU(cudaFree(ctx->d_classes32));
+        ctx->d_classes32_cap = (u32)std::max<size_t>(blob32.size() * 2, 4096);
+        CU(cudaMalloc(&ctx->d_classes32, ctx->d_classes32_cap));
+    }
+    CU(cudaMemcpyAsync(ctx->d_classes32, blob32.data(), blob32.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const bool q_changed = ctx->Q != n_classes;
     ctx->classes.assign(classes, classes + n_classes);
@@ -1766,14 +1963,6 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
     if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
     if (ctx->dag) return fail(ctx, HQS_E_STATE, "hqs_ready_push is not available after hqs_dag_load");
     CU(cudaSetDevice(ctx->device));
-    u32 max_h = 0, max_c = 0;
-    for (u32 i = 0; i < n; ++i) { max_h = std::max(max_h, task[i]); max_c = std::max(max_c, class_id[i]); }
-    if (max_c >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", max_c, ctx->Q);
-    if (max_h == ~0u) return fail(ctx, HQS_E_INVALID, "task handle 0xFFFFFFFF is reserved");
-    int rc = ensure_handles(ctx, max_h + 1);
-    if (rc) return rc;
-    ctx->n_handles = std::max(ctx->n_handles, max_h + 1);
-    ctx->stats.n_handles = ctx->n_handles;
     if (n > ctx->push_cap) {
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_push_task) { CU(cudaFree(ctx->d_push_task)); CU(cudaFree(ctx->d_push_cls)); CU(cudaFree(ctx->d_push_prio)); }
@@ -1785,6 +1974,18 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
     CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_push_cls, class_id, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_push_prio, priority, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // validate on the host while the staging copies are in flight (they touch no scheduler state)
+    u32 max_h = 0, max_c = 0;
+    max_of_u32_pair(task, class_id, n, &max_h, &max_c);
+    if (max_c >= ctx->Q || max_h == ~0u) {
+        cudaStreamSynchronize(ctx->stream);      // the caller may free its arrays as soon as we return
+        if (max_c >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", max_c, ctx->Q);
+        return fail(ctx, HQS_E_INVALID, "task handle 0xFFFFFFFF is reserved");
+    }
+    int rc = ensure_handles(ctx, max_h + 1);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    ctx->n_handles = std::max(ctx->n_handles, max_h + 1);
+    ctx->stats.n_handles = ctx->n_handles;
     CU(cudaMemsetAsync(ctx->d_newcnt, 0, sizeof(u32), ctx->stream));
     push_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_key,
                                                      ctx->d_prio, ctx->d_levels, (u32)ctx->dev_levels.size(),

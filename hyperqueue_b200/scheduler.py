@@ -72,11 +72,11 @@ class WorkerTaskMapping:
 
 
 class GpuScheduler:
-    def __init__(self, n_resources: int, device: int = 0) -> None:
+    def __init__(self, n_resources: int, device: int = 0, flags: int = 0) -> None:
         self._lib = L.load_library()
         self.R = int(n_resources)
         self._ctx = C.c_void_p()
-        rc = self._lib.hqs_create(C.byref(self._ctx), device, self.R, 0)
+        rc = self._lib.hqs_create(C.byref(self._ctx), device, self.R, int(flags))
         if rc:
             raise L.HqsError(rc, (self._lib.hqs_last_error(None) or b"").decode())
         self._rq_ids: Dict[Tuple[RequestVariant, ...], int] = {}

@@ -100,11 +100,19 @@ typedef struct {
     uint64_t ticks;
     uint32_t n_handles;         /* size of the device task table                                  */
     uint32_t coarsened;         /* 1 if priority levels had to be merged to fit HQS_MAX_GROUPS    */
+    uint32_t narrow_amounts;    /* 1 if the last tick solved on gcd-scaled 32-bit amounts          */
+    uint32_t reserved;
 } hqs_stats;
 
 int hqs_abi_version(void);
 
-/* Creates a context on CUDA device `device`.  n_resources = number of resource kinds (R <= 16). */
+/* Creates a context on CUDA device `device`.  n_resources = number of resource kinds (R <= 16).
+ * flags: bit 0 = no packing of the first saturated priority level (plain first-fit everywhere);
+ *        bit 1 = always solve on 64-bit amounts (default: amounts are divided by the per-resource gcd of
+ *                the requested amounts and solved in 32 bits whenever every scaled amount of the tick is
+ *                below 2^31 — same results, shorter critical path).  Both bits exist for tests. */
+#define HQS_CREATE_NO_PACK 1u
+#define HQS_CREATE_WIDE_AMOUNTS 2u
 int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags);
 void hqs_destroy(hqs_ctx* ctx);
 const char* hqs_last_error(const hqs_ctx* ctx);   /* ctx may be NULL: last error of hqs_create */

@@ -31,16 +31,25 @@ def _random_workload(n, w, q, r, vmax, seed, n_prio=5, cap=(8, 64)):
                       rng.integers(0, n_prio, n).astype(np.int32))
 
 
-def _check_exact(wl):
-    s = P.gpu_scheduler(wl)
-    fb = s.free.copy()
-    m = s.run_scheduling()
-    assert P.judge_tick(wl, fb, m.assignments).ok
-    exp, exp_free = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), fb)
-    assert np.array_equal(m.assignments, exp)
-    assert np.array_equal(m.free_after, exp_free)
-    s.close()
-    return m
+def _check_exact(wl, expect_narrow=None):
+    """Both amount widths of the solver (gcd-scaled 32-bit and plain 64-bit) against the sequential spec."""
+    out = None
+    for flags in (0, 2):
+        s = P.gpu_scheduler(wl, flags=flags)
+        fb = s.free.copy()
+        m = s.run_scheduling()
+        assert P.judge_tick(wl, fb, m.assignments).ok
+        exp, exp_free = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), fb)
+        assert np.array_equal(m.assignments, exp)
+        assert np.array_equal(m.free_after, exp_free)
+        narrow = s.stats()["narrow_amounts"]
+        if flags == 2:
+            assert narrow == 0
+        elif expect_narrow is not None:
+            assert narrow == int(expect_narrow)
+        s.close()
+        out = out or m
+    return out
 
 
 def test_maximum_workers_resources_variants():
@@ -170,3 +179,44 @@ def test_new_worker_query_is_a_dry_run():
     real = s.run_scheduling()
     assert real.n_assigned() > 0                                          # and the real tick still sees every task
     s.close()
+
+
+def test_narrow_amounts_with_remainders_and_all_policy():
+    # requests are multiples of 4 units (gcd 4 * FR), worker amounts are not: the scaled solver carries the
+    # remainders; an `All` request needs free == total exactly, remainder included
+    rng = np.random.default_rng(11)
+    classes = [[{"amounts": {0: 4 * FR, 1: 8 * FR}}], [{"amounts": {0: 8 * FR}, "all": (2,)}],
+               [{"amounts": {1: 4 * FR, 2: 12 * FR}}], [{"amounts": {0: 12 * FR, 2: 4 * FR}}, {"amounts": {1: 16 * FR}}]]
+    w = 48
+    total = rng.integers(20, 90, size=(w, 3)).astype(np.uint64) * np.uint64(FR) + rng.integers(0, FR, size=(w, 3)).astype(np.uint64)
+    free = total.copy()
+    free[::3, 2] -= np.uint64(1)            # a touched resource: `All` on it must not fit there
+    free[1::3, 0] -= np.uint64(4 * FR)
+    wl = P.Workload(3, classes, total, free, rng.integers(0, 4, 3000).astype(np.uint32), rng.integers(0, 3, 3000).astype(np.int32))
+    m = _check_exact(wl, expect_narrow=True)
+    assert m.n_assigned() > 50
+
+
+def test_amounts_beyond_31_bits_use_the_wide_solver():
+    # memory in bytes with odd request sizes: gcd 1 and totals ~ 2^50 => not representable in the narrow form
+    rng = np.random.default_rng(12)
+    gib = 1 << 30
+    classes = [[{"amounts": {0: 1 * FR, 1: (3 * gib + 1) * FR}}], [{"amounts": {0: 2 * FR, 1: (5 * gib + 7) * FR}}],
+               [{"amounts": {1: 11 * gib * FR}}]]
+    w = 20
+    total = np.stack([np.full(w, 64 * FR, dtype=np.uint64), rng.integers(200, 900, size=w).astype(np.uint64) * np.uint64(gib * FR)], axis=1)
+    wl = P.Workload(2, classes, total, total.copy(), rng.integers(0, 3, 5000).astype(np.uint32), rng.integers(0, 4, 5000).astype(np.int32))
+    m = _check_exact(wl, expect_narrow=False)
+    assert m.n_assigned() > 100
+
+
+def test_large_amounts_with_a_common_factor_stay_narrow():
+    # the same memory sizes in whole GiB: the per-resource gcd brings them back under 2^31
+    rng = np.random.default_rng(13)
+    gib = 1 << 30
+    classes = [[{"amounts": {0: 1 * FR, 1: 3 * gib * FR}}], [{"amounts": {0: 2 * FR, 1: 5 * gib * FR}}], [{"amounts": {1: 11 * gib * FR}}]]
+    w = 20
+    total = np.stack([np.full(w, 64 * FR, dtype=np.uint64), rng.integers(200, 900, size=w).astype(np.uint64) * np.uint64(gib * FR) + np.uint64(12345)], axis=1)
+    wl = P.Workload(2, classes, total, total.copy(), rng.integers(0, 3, 5000).astype(np.uint32), rng.integers(0, 4, 5000).astype(np.int32))
+    m = _check_exact(wl, expect_narrow=True)
+    assert m.n_assigned() > 100

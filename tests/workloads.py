@@ -159,9 +159,9 @@ def dag_csr(deps: List[List[int]]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
 
 
 
-def gpu_scheduler(wl: Workload, add_tasks: bool = True, device: int = 0):
+def gpu_scheduler(wl: Workload, add_tasks: bool = True, device: int = 0, flags: int = 0):
     from hyperqueue_b200 import GpuScheduler, RequestVariant, priority_from_user
-    s = GpuScheduler(wl.R, device)
+    s = GpuScheduler(wl.R, device, flags)
     for c, vs in enumerate(wl.classes):
         rid = s.get_or_create_resource_rq_id([RequestVariant.of(d["amounts"], d.get("all", ()), d.get("weight", 1.0),
                                                                 d.get("min_time_s", 0.0)) for d in vs])

@@ -15,7 +15,7 @@ from workloads import gpu_scheduler
 from bench import make_workload
 from hyperqueue_b200 import priority_from_user
 
-lib = L.load()
+lib = L.load_library()
 N, W = 1_000_000, 256
 wl = make_workload(N, seed=0)
 s = gpu_scheduler(wl, add_tasks=False)
