@@ -24,6 +24,12 @@ CASES = {
     "indep_8000_16_16_2": ("indep", [8000, 16, 16, 2], {}),
     "indep3_3000_8_6_3": ("indep", [3000, 8, 6, 3], {"variants3": True}),
     "dag_6000_8_6_4": ("dag", [6000, 8, 6, 4], {"window": 512}),
+    # held-out cases added after the packing heuristics were fixed (validation, not tuning)
+    "indep3_4000_12_8_7": ("indep", [4000, 12, 8, 7], {"variants3": True}),
+    "indep3_3000_8_6_9": ("indep", [3000, 8, 6, 9], {"variants3": True}),
+    "indep3_5000_16_10_11": ("indep", [5000, 16, 10, 11], {"variants3": True}),
+    "indep_6000_10_10_13": ("indep", [6000, 10, 10, 13], {}),
+    "indep3_2500_6_5_21": ("indep", [2500, 6, 5, 21], {"variants3": True}),
 }
 
 out = {}

@@ -8,12 +8,16 @@ The algorithm, per tick:
   levels (distinct priorities, descending) x classes (the tick's class order) = groups; groups are
   processed in that order.  The FIRST level whose demand exceeds the aggregate free capacity is
   "packed": the level's class counts are pre-split over the workers (share proportional to how many
-  tasks of the class fit on the worker alone) and every worker then fills ITSELF, independently, by
-  repeatedly taking the candidate (class, variant) best aligned with its remaining capacity (normalised
-  dot product, the vector-bin-packing heuristic) — this is what makes one tick use cpus, gpus and memory
-  together the way the reference's MILP objective (sum of normalised utilisations, solver.rs:520-549)
-  does.  Everything else — levels before and after, and whatever the packed level could not place — is
-  priority-ordered first-fit over workers in ascending id (compaction, solver.rs (n - w_idx)/n).
+  tasks of the class fit on the worker alone, scaled by phi = the fraction of the level's demand the
+  pool can serve, so that every class of the level progresses at the same rate) and every worker then
+  fills ITSELF, independently: per class it considers the variant that costs the smallest share of what
+  the worker has left (min over variants of max_r amount_r / free_r), and takes from the class whose such
+  variant is best aligned with its remaining capacity (normalised dot product, the vector-bin-packing
+  heuristic) — this is what makes one tick use cpus, gpus and memory together the way the reference's
+  MILP objective (sum of normalised utilisations, solver.rs:520-549) does.  Everything else — levels
+  before and after, and whatever the packed level could not place — is priority-ordered first-fit over
+  workers in ascending id (compaction, solver.rs (n - w_idx)/n); a worker tries the variants of a class in
+  ascending order of the same "share of what I have left" cost, re-evaluated after each variant.
 Mirrors class_order(), solve_body() / pack_body(), emit_k().
 """
 from __future__ import annotations
@@ -126,6 +130,34 @@ class _Tick:
                 cnt = min(cnt, fr[r] // self.am[c][v][r])
         return cnt
 
+    def next_variant(self, w: int, c: int, tried: int) -> int:
+        """The untried variant of class c that costs the smallest share of what worker w has left:
+        min over variants of max_r f32(amount_r) * (1 / f32(free_r)) in IEEE single (u64 -> double -> single,
+        both round-to-nearest); a variant with an `All` entry costs +inf; ties: lower variant index."""
+        nv = len(self.am[c])
+        if nv == 1:
+            return 0
+        fr = self.fr[w]
+        best, best_d = -1, np.float32(0)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            inv = [np.float32(1.0) / np.float32(float(fr[r])) for r in range(self.R)]
+            for v in range(nv):
+                if (tried >> v) & 1:
+                    continue
+                dom = np.float32(0)
+                if self.alls[c][v]:
+                    dom = np.float32(np.inf)
+                else:
+                    for r in range(self.R):
+                        a = self.am[c][v].get(r)
+                        if a is None or fr[r] == AMOUNT_MAX:
+                            continue
+                        x = np.float32(float(a)) * inv[r]
+                        dom = x if x > dom else dom
+                if best < 0 or dom < best_d:
+                    best, best_d = v, dom
+        return best
+
     def take(self, w: int, c: int, v: int, k: int) -> None:
         fr = self.fr[w]
         for r in range(self.R):
@@ -141,9 +173,11 @@ class _Tick:
                 fr[r] += k * a
 
 
-def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[List[int]]) -> bool:
+def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[List[int]]) -> Tuple[bool, float]:
     """Demand of the level (each class with its first variant of the tick's variant order) against the
-    aggregate free capacity, exact saturating u64 arithmetic."""
+    aggregate free capacity, exact saturating u64 arithmetic.  Returns (saturated, phi) with
+    phi = min(1, min_r capacity_r / demand_r) in IEEE double (u64 -> double round-to-nearest) when at
+    least two resources are over-subscribed, else 1."""
     R, W = t.R, t.W
     C = [0] * R
     for r in range(R):
@@ -161,10 +195,33 @@ def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[Li
             continue            # no worker is big enough for it: it is not demand that capacity could serve
         for r, a in am.items():
             D[r] = _sat_add(D[r], _sat_mul(n, a))
-    return any(C[r] != U64 and D[r] > C[r] for r in range(R))
+    n_sat = sum(1 for r in range(R) if C[r] != U64 and D[r] > C[r])
+    phi = 1.0
+    if n_sat >= 2:
+        # two or more scarce resources: classes complement each other, so each gets the same fraction of its
+        # demand this tick.  With a single scarce resource every split drains at the same rate and the
+        # alignment order alone (the reference objective's preference) decides.
+        for r in range(R):
+            if C[r] != U64 and D[r] > 0:
+                x = float(C[r]) / float(D[r])
+                phi = x if x < phi else phi
+    return n_sat > 0, phi
 
 
-def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int], List[int]]:
+def _dom_share64(t: _Tick, w: int, c: int, v: int, inv_fr: List[float]) -> float:
+    """max_r amount_r * (1 / free_r) in double: the share of what the worker has left that one task costs."""
+    dom = 0.0
+    fr = t.fr[w]
+    for r in range(t.R):
+        a = t.am[c][v].get(r)
+        if a is None or fr[r] == AMOUNT_MAX:
+            continue
+        x = float(a) * inv_fr[r]
+        dom = x if x > dom else dom
+    return dom
+
+
+def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tuple[int, int], List[int]]:
     """Every worker fills itself (its free vector is consumed).  Returns taken[(group index, variant)][w]."""
     W, R = t.W, t.R
     cands = [(gi, c, v) for gi, (c, n) in enumerate(groups) for v in range(len(t.am[c]))]
@@ -175,7 +232,7 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int]
         T = sum(cn)
         if T:
             for w in range(W):
-                quota[w][gi] = -(-n * cn[w] // T)
+                quota[w][gi] = int(math.ceil(float(-(-n * cn[w] // T)) * phi))
     # b. every worker fills itself
     taken: Dict[Tuple[int, int], int] = {}       # (w, candidate index) -> count
     for w in range(W):
@@ -196,11 +253,20 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]]) -> Dict[Tuple[int, int]
         for _ in range(PACK_MAX_ITER):
             fr = t.fr[w]
             u = [float(fr[r]) * inv_tot[r] for r in range(R)]
-            best, best_s = -1, 0.0
+            inv_fr = [(1.0 / float(fr[r])) if fr[r] != 0 else float("inf") for r in range(R)]
+            # per group: the feasible variant with the smallest dominant share (ties: lower candidate index)
+            pick: Dict[int, Tuple[float, int]] = {}
             for ci, (gi, c, v) in enumerate(cands):
                 if quota[w][gi] <= 0 or not t.admissible(w, c, v):
                     continue
                 if any(fr[r] != AMOUNT_MAX and a > fr[r] for r, a in t.am[c][v].items()):
+                    continue
+                dom = _dom_share64(t, w, c, v, inv_fr)
+                if gi not in pick or dom < pick[gi][0]:
+                    pick[gi] = (dom, ci)
+            best, best_s = -1, 0.0
+            for ci, (gi, c, v) in enumerate(cands):
+                if gi not in pick or pick[gi][1] != ci:
                     continue
                 dot = 0.0
                 for r in range(R):
@@ -249,9 +315,11 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
         if not packed:
             n_cand = sum(len(t.am[c]) for c, _ in groups)
             has_all = any(t.alls[c][v] for c, _ in groups for v in range(len(t.am[c])))
-            if n_cand <= PACK_MAX_CAND and not has_all and _level_is_saturated(t, groups, vorder):
-                taken = _pack_level(t, groups)
-                packed = True
+            if n_cand <= PACK_MAX_CAND and not has_all:
+                saturated, phi = _level_is_saturated(t, groups, vorder)
+                if saturated:
+                    taken = _pack_level(t, groups, phi)
+                    packed = True
         for gi, (c, n) in enumerate(groups):
             tasks = tasks_of[c]
             pos = 0
@@ -272,12 +340,16 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
                         out.append((tt, w, v, 0))
                     pos += use
             remaining = n - pos
-            for v in vorder[c]:
+            nv = len(t.am[c])
+            tried = [0] * W
+            for vi in range(nv):
                 if remaining == 0:
                     break
                 for w in range(W):
                     if remaining == 0:
                         break
+                    v = t.next_variant(w, c, tried[w])
+                    tried[w] |= 1 << v
                     cnt = t.fit(w, c, v, remaining)
                     if cnt <= 0:
                         continue

@@ -122,27 +122,21 @@ def test_many_priority_levels_are_coarsened_not_rejected():
 # ---------------------------------------------------------------------------------------------------
 # drain (mode M2): feasibility every tick, resources conserved, makespan
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("key", ["indep_4000_8_6_0", "indep_8000_16_8_1", "indep_6000_12_12_5"])
+ALL_DRAINS = sorted(json.load(open(GOLDEN)).keys())
+
+
+@pytest.mark.parametrize("key", ALL_DRAINS)
 def test_drain_makespan_vs_oracle(key):
-    golden = json.load(open(GOLDEN))[key]
-    wl = P.make_independent(*golden["args"])
-    ticks, per_tick = P.gpu_drain(wl)
-    assert sum(per_tick) == wl.n_tasks
-    assert ticks == G.model_drain(wl)[0]
-    # north_star: makespan within 2 % of the reference scheduler
-    assert abs(ticks - golden["oracle_ticks"]) <= max(1, 0.02 * golden["oracle_ticks"]), (ticks, golden)
-
-
-@pytest.mark.parametrize("key", ["indep_8000_16_16_2", "indep3_3000_8_6_3", "dag_6000_8_6_4"])
-def test_drain_makespan_known_gap(key):
-    """Configurations where the first-fit heuristic does not yet match the MILP's packing: the measured
-    gap is pinned (DESIGN.md "parity status") so that it can only shrink."""
+    """north_star: the zero-duration drain takes at most 2 % more ticks than the reference scheduler (finishing
+    earlier is fine).  Six cases were used while designing the packing rules, five (see make_oracle_drains.py)
+    were generated afterwards as held-out checks."""
     golden = json.load(open(GOLDEN))[key]
     wl = (P.make_dag if key.startswith("dag") else P.make_independent)(*golden["args"], **golden.get("kwargs", {}))
     ticks, per_tick = P.gpu_drain(wl)
     assert sum(per_tick) == wl.n_tasks
     assert ticks == G.model_drain(wl)[0]
-    assert ticks <= golden["max_ticks"], (ticks, golden)
+    assert ticks <= golden["max_ticks"], (ticks, golden)                       # the pinned value can only shrink
+    assert ticks - golden["oracle_ticks"] <= 0.02 * golden["oracle_ticks"], (ticks, golden)
 
 
 def test_dag_drain_readiness_propagation():
