@@ -237,7 +237,7 @@ constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: a stuck grid 
 template <int RT, typename AT = u64>
 struct VarT {
     AT amount[RT];
-    float rcpf[sizeof(AT) == 8 ? 2 * RT : RT];  // [0, RT): fp32 1.0 / amount (0 where unused); rest: padding
+    float rcpf[2 * RT];  // [0, RT): fp32 1.0 / amount (0 where unused); [RT, 2 RT): fp32 of the exact amount
     u64 min_time_ms;
     u32 all_mask;
     u32 used_mask;
@@ -416,7 +416,9 @@ __device__ __forceinline__ void take_from(AT (&fr)[RT], const VarT<RT, AT>& dv, 
 
 // ---- pack: one warp fills one worker (specification: tests/greedy_model.py::_pack_level step b) ----
 template <int RT>
-__device__ void pack_body(const SolveArgs& a) {
+__device__ void pack_body(const SolveArgs& a, unsigned char* smem_dyn) {
+    // per-warp scratch in the (otherwise unused) dynamic shared memory of the pack CTAs
+    double* s_dom = reinterpret_cast<double*>(smem_dyn) + (size_t)(threadIdx.x >> 5) * PACK_MAX_CAND;
     const ClassT<RT>* classes = reinterpret_cast<const ClassT<RT>*>(a.classes64);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 n_pack_ctas = gridDim.x - 1;
@@ -443,7 +445,7 @@ __device__ void pack_body(const SolveArgs& a) {
         for (int r = 0; r < RT; ++r)
             inv_tot[r] = (tot[r] != 0 && tot[r] != HQS_AMOUNT_MAX) ? __ddiv_rn(1.0, to_double(tot[r])) : 0.0;
         // my two candidates
-        u32 cls[2], var[2], gi[2], quota[2], taken[2];
+        u32 cls[2], var[2], gi[2], quota[2], taken[2], gs[2], ge[2];
         bool live[2];
         double inv_norm[2], dvec[2][RT];
         const VarT<RT>* dv[2];
@@ -452,12 +454,15 @@ __device__ void pack_body(const SolveArgs& a) {
             const u32 ci = lane + 32 * j;
             live[j] = ci < n_cand;
             taken[j] = 0; quota[j] = 0; inv_norm[j] = 0.0; cls[j] = var[j] = gi[j] = 0; dv[j] = &classes[0].v[0];
+            gs[j] = ge[j] = 0;
 #pragma unroll
             for (int r = 0; r < RT; ++r) dvec[j][r] = 0.0;
             if (live[j]) {
                 const u32 cd = __ldcg(a.pk.cand + ci);
                 cls[j] = cd & 0xFFFFu; var[j] = (cd >> 16) & 0xFFu; gi[j] = cd >> 24;
                 dv[j] = &classes[cls[j]].v[var[j]];
+                gs[j] = ci - var[j];                                  // the variants of a group are consecutive candidates
+                ge[j] = gs[j] + classes[cls[j]].n_variants;
                 quota[j] = __ldcg(a.pk.quota + (size_t)w * PACK_MAX_CAND + gi[j]);
                 const uint8_t blk = a.blocked ? a.blocked[(size_t)w * a.Q + cls[j]] : 0;
                 live[j] = admissible(*dv[j], var[j], blk, rem_time);
@@ -472,27 +477,53 @@ __device__ void pack_body(const SolveArgs& a) {
             }
         }
         for (u32 it = 0; it < PACK_MAX_ITER; ++it) {
-            double u[RT];
+            double u[RT], inv_u[RT];
 #pragma unroll
-            for (int r = 0; r < RT; ++r) u[r] = __dmul_rn(to_double(fr[r]), inv_tot[r]);
+            for (int r = 0; r < RT; ++r) {
+                u[r] = __dmul_rn(to_double(fr[r]), inv_tot[r]);
+                inv_u[r] = __ddiv_rn(1.0, u[r]);                      // +inf where nothing is left
+            }
+            // a. per candidate: feasible? its dominant share of what the worker has left
+            bool elig[2];
+            double dom[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                elig[j] = live[j] && quota[j] != 0;
+                dom[j] = 0.0;
+                if (elig[j]) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        if (((dv[j]->used_mask >> r) & 1) && fr[r] != HQS_AMOUNT_MAX && dv[j]->amount[r] > fr[r]) elig[j] = false;
+                        if (dvec[j][r] > 0.0) {
+                            const double x = __dmul_rn(dvec[j][r], inv_u[r]);
+                            dom[j] = x > dom[j] ? x : dom[j];
+                        }
+                    }
+                }
+                if (lane + 32 * j < PACK_MAX_CAND) s_dom[lane + 32 * j] = elig[j] ? dom[j] : -1.0;   // -1: not eligible
+            }
+            __syncwarp();
+            // b. per group the eligible variant with the smallest share (ties: lower index) stays in the race
             double best_s = 0.0;
             u32 best_ci = ~0u;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                if (!live[j] || quota[j] == 0) continue;
-                bool fits = true;
+                if (!elig[j]) continue;
+                const u32 ci = lane + 32 * j;
+                bool win = true;
+                for (u32 k = gs[j]; k < ge[j]; ++k) {
+                    const double o = s_dom[k];
+                    if (k != ci && o >= 0.0 && (o < dom[j] || (o == dom[j] && k < ci))) win = false;
+                }
+                if (!win) continue;
                 double dot = 0.0;
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    if (((dv[j]->used_mask >> r) & 1) && fr[r] != HQS_AMOUNT_MAX && dv[j]->amount[r] > fr[r]) fits = false;
-                    dot = __dadd_rn(dot, __dmul_rn(dvec[j][r], u[r]));
-                }
-                if (!fits) continue;
-                const double s = __dmul_rn(dot, inv_norm[j]);
-                const u32 ci = lane + 32 * j;
-                if (best_ci == ~0u || s > best_s) { best_s = s; best_ci = ci; }   // j = 0 first: lower index wins ties
+                for (int r = 0; r < RT; ++r) dot = __dadd_rn(dot, __dmul_rn(dvec[j][r], u[r]));
+                const double sc = __dmul_rn(dot, inv_norm[j]);
+                if (best_ci == ~0u || sc > best_s) { best_s = sc; best_ci = ci; }   // j = 0 first: lower index wins ties
             }
-            // warp argmax: larger score, ties to the lower candidate index
+            __syncwarp();
+            // c. warp argmax: larger score, ties to the lower candidate index
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) {
                 const double os = __shfl_xor_sync(0xffffffffu, best_s, d);
@@ -804,12 +835,22 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
             const u32 n_cand = (u32)(meta & 0xFFFFFFFFu);
             const bool has_all = (meta >> 32) != 0;
             if (n_cand <= PACK_MAX_CAND && !has_all) {
-                bool saturated = false;
+                // phi = the fraction of the level's demand the pool can serve, when two or more resources are
+                // over-subscribed (the classes then complement each other and each gets the same fraction of
+                // its demand this tick); with a single scarce resource any split drains at the same rate
+                u32 n_sat = 0;
+                double phi = 1.0;
                 for (u32 r = 0; r < a.R; ++r) {
                     const u64 C = __shfl_sync(0xffffffffu, tot_v, r);
                     const u64 D = __shfl_sync(0xffffffffu, tot_v, RT + r);
-                    if (C != HQS_AMOUNT_MAX && D > C) saturated = true;
+                    if (C != HQS_AMOUNT_MAX && D > C) n_sat++;
+                    if (C != HQS_AMOUNT_MAX && D > 0) {
+                        const double x = __ddiv_rn(__ull2double_rn(C), __ull2double_rn(D));
+                        phi = x < phi ? x : phi;
+                    }
                 }
+                if (n_sat < 2) phi = 1.0;
+                const bool saturated = n_sat != 0;
                 if (saturated) {
                     // ---- a. quotas: share of each class proportional to how many fit on the worker alone
                     for (u32 e = li; e < lj; ++e) {
@@ -835,7 +876,8 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                         for (u32 w2 = 0; w2 < nwarps; ++w2) T += buf[w2];
                         if (has_worker) {
                             const u64 q = T ? ((u64)n * cn + T - 1) / T : 0;
-                            a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)] = (u32)q;
+                            const u64 q_phi = __double2ull_ru(__dmul_rn(__ull2double_rn(q), phi));     // ceil(q * phi)
+                            a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)] = (u32)q_phi;
                         }
                     }
                     // ---- b. publish the worker state and the candidate list, release the pack warps
@@ -931,8 +973,36 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                 }
                 cand_base += nv;
             }
+            u32 tried = 0;                                            // per worker: variants of this class already offered
             for (u32 vi = 0; vi < nv && remaining > 0; ++vi) {
-                const u32 v = vorder[c * HQS_MAX_VARIANTS + vi];
+                // Each worker offers the untried variant that costs the smallest share of what it has left:
+                // min over variants of max_r f32(amount_r) * (1 / f32(free_r)), `All` = +inf, ties to the lower
+                // variant id (specification: tests/greedy_model.py::_Tick.next_variant).
+                u32 v = 0;
+                if (nv > 1) {
+                    float inv[RT];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) inv[r] = __fdiv_rn(1.0f, __double2float_rn(__ull2double_rn(exact_free(r))));
+                    float best_d = 0.0f;
+                    int best_v = -1;
+                    for (u32 vv = 0; vv < nv; ++vv) {
+                        if ((tried >> vv) & 1) continue;
+                        const Var& cv = classes[c].v[vv];
+                        float dom = 0.0f;
+                        if (cv.all_mask) dom = __int_as_float(0x7f800000);
+                        else {
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) {
+                                if (!((cv.used_mask >> r) & 1) || fr[r] == AMAX) continue;
+                                const float x = __fmul_rn(cv.rcpf[RT + r], inv[r]);
+                                dom = x > dom ? x : dom;
+                            }
+                        }
+                        if (best_v < 0 || dom < best_d) { best_v = (int)vv; best_d = dom; }
+                    }
+                    v = (u32)best_v;
+                    tried |= 1u << v;
+                }
                 const Var& dv = classes[c].v[v];
                 FLUSH_SEGMENTS_IF_FULL();
                 // exact count once (reciprocal division, capped at `remaining`): can1 = cnt > 0, and the
@@ -1108,7 +1178,7 @@ __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
     }
     __syncthreads();
     if (s_cmd == PHASE_PACK) {
-        pack_body<RT>(a);
+        pack_body<RT>(a, smem_dyn);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(&a.sync->done, 1u);
@@ -1737,6 +1807,7 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.smem_glist_cap = std::min<u32>(t.G, 2048);
     solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + 32;
     solve_smem += (size_t)a.smem_glist_cap * sizeof(GroupOut) + 2 * SEG_SMEM * sizeof(u32);
+    solve_smem = std::max(solve_smem, (size_t)nw * PACK_MAX_CAND * sizeof(double));     // pack warps' scratch
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
     void* kargs[] = {&a};
     const bool small = a.smem_classes != 0;
@@ -1873,6 +1944,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                 if (r < RT) {
                     amount[r] = all ? 0 : amt;
                     rcp[r] = (!all && amt) ? 1.0f / (float)amt : 0.0f;
+                    rcp[RT + r] = all ? 0.0f : (float)(double)amt;          // u64 -> double -> float, both RN
                 }
                 if (all || amt) used |= 1u << r;
             }
@@ -1900,7 +1972,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                 if (!((classes[c].variants[v].all_mask >> r) & 1) && classes[c].variants[v].amount[r])
                     gs[r] = std::gcd(gs[r], (u64)classes[c].variants[v].amount[r]);
     bool narrow_ok = true;
-    const size_t var_bytes32 = (size_t)RT * 8 + 16, cls_bytes32 = ctx->class_bytes32;
+    const size_t var_bytes32 = (size_t)RT * 12 + 16, cls_bytes32 = ctx->class_bytes32;
     std::vector<unsigned char> blob32((size_t)n_classes * cls_bytes32, 0);
     for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) {
         if (gs[r] == 0) gs[r] = 1;
@@ -1915,8 +1987,8 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
             unsigned char* vb = cb + 8 + (size_t)v * var_bytes32;
             u32* amount = reinterpret_cast<u32*>(vb);
             float* rcp = reinterpret_cast<float*>(vb + (size_t)RT * 4);
-            u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 8);
-            u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 8 + 8);
+            u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 12);
+            u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 12 + 8);
             u32 used = 0;
             for (u32 r = 0; r < ctx->R; ++r) {
                 const bool all = (sc.variants[v].all_mask >> r) & 1;
@@ -1924,6 +1996,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                 if (amt > NARROW_LIMIT) narrow_ok = false;
                 amount[r] = (u32)amt;
                 rcp[r] = amt ? 1.0f / (float)(u32)amt : 0.0f;
+                rcp[RT + r] = all ? 0.0f : (float)(double)sc.variants[v].amount[r];
                 if (all || sc.variants[v].amount[r]) used |= 1u << r;
             }
             *min_time = sc.variants[v].min_time_ms;

@@ -208,19 +208,6 @@ def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[Li
     return n_sat > 0, phi
 
 
-def _dom_share64(t: _Tick, w: int, c: int, v: int, inv_fr: List[float]) -> float:
-    """max_r amount_r * (1 / free_r) in double: the share of what the worker has left that one task costs."""
-    dom = 0.0
-    fr = t.fr[w]
-    for r in range(t.R):
-        a = t.am[c][v].get(r)
-        if a is None or fr[r] == AMOUNT_MAX:
-            continue
-        x = float(a) * inv_fr[r]
-        dom = x if x > dom else dom
-    return dom
-
-
 def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tuple[int, int], List[int]]:
     """Every worker fills itself (its free vector is consumed).  Returns taken[(group index, variant)][w]."""
     W, R = t.W, t.R
@@ -253,7 +240,7 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tup
         for _ in range(PACK_MAX_ITER):
             fr = t.fr[w]
             u = [float(fr[r]) * inv_tot[r] for r in range(R)]
-            inv_fr = [(1.0 / float(fr[r])) if fr[r] != 0 else float("inf") for r in range(R)]
+            inv_u = [(1.0 / u[r]) if u[r] != 0.0 else float("inf") for r in range(R)]
             # per group: the feasible variant with the smallest dominant share (ties: lower candidate index)
             pick: Dict[int, Tuple[float, int]] = {}
             for ci, (gi, c, v) in enumerate(cands):
@@ -261,7 +248,12 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tup
                     continue
                 if any(fr[r] != AMOUNT_MAX and a > fr[r] for r, a in t.am[c][v].items()):
                     continue
-                dom = _dom_share64(t, w, c, v, inv_fr)
+                # dominant share of what the worker has left: max_r (amount_r / total_r) * (1 / (free_r / total_r))
+                dom = 0.0
+                for r in range(R):
+                    if dvec[ci][r] > 0.0:
+                        x = dvec[ci][r] * inv_u[r]
+                        dom = x if x > dom else dom
                 if gi not in pick or dom < pick[gi][0]:
                     pick[gi] = (dom, ci)
             best, best_s = -1, 0.0
