@@ -365,8 +365,9 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], const u64 (&tot)[R
     return cnt;
 }
 
-// Narrow amounts (< 2^31): one conversion, one multiply and a single +-1 fix-up per resource — the fp32 estimate
-// of a quotient below 2^20 is off by less than one (relative error < 2^-22).
+// Narrow amounts (< 2^31): one conversion, one multiply and a single +1 fix-up per resource.  The host stores
+// rcpf = (1 / amount) * (1 - 2^-21): with every rounding counted the estimate is then never above the true
+// quotient and, for quotients below 2^20, less than one below it, so floor(estimate) is q or q - 1.
 template <int RT>
 __device__ __forceinline__ u64 fit_count(const u32 (&fr)[RT], const u32 (&tot)[RT], u32 allok, const VarT<RT, u32>& dv,
                                          u64 cap64) {
@@ -374,20 +375,33 @@ __device__ __forceinline__ u64 fit_count(const u32 (&fr)[RT], const u32 (&tot)[R
     u32 cnt = cap;
     bool big = false;
     const u32 used = dv.used_mask, allm = dv.all_mask;
+    if (allm == 0) {
+        // no `All` entry (the usual case): an unused resource has amount 0, which "fits cap" by itself
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-        const bool on = (used >> r) & 1, all = (allm >> r) & 1;
-        const u32 n = fr[r], d = dv.amount[r];
-        const bool fits_cap = (u64)d * cap <= (u64)n;
-        const float qf = __uint2float_rn(n) * dv.rcpf[r];
-        u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
-        const u32 p = q * d;
-        q = p > n ? q - 1 : (n - p >= d ? q + 1 : q);
-        const u32 q_all = (((allok >> r) & 1) && n == tot[r]) ? 1u : 0u;
-        const bool unconstrained = !on || (!all && (n == 0xFFFFFFFFu || fits_cap));
-        big |= on && !all && !unconstrained && qf >= 1048576.0f;
-        const u32 qr = all ? q_all : q;
-        cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
+        for (int r = 0; r < RT; ++r) {
+            const u32 n = fr[r], d = dv.amount[r];
+            const bool unconstrained = (u64)d * cap <= (u64)n || n == 0xFFFFFFFFu;
+            const float qf = __uint2float_rn(n) * dv.rcpf[r];
+            u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
+            q += (n - q * d >= d) ? 1u : 0u;
+            big |= !unconstrained && qf >= 1048576.0f;
+            cnt = unconstrained ? cnt : (cnt < q ? cnt : q);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const bool on = (used >> r) & 1, all = (allm >> r) & 1;
+            const u32 n = fr[r], d = dv.amount[r];
+            const bool fits_cap = (u64)d * cap <= (u64)n;
+            const float qf = __uint2float_rn(n) * dv.rcpf[r];
+            u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
+            q += (n - q * d >= d) ? 1u : 0u;
+            const u32 q_all = (((allok >> r) & 1) && n == tot[r]) ? 1u : 0u;
+            const bool unconstrained = !on || (!all && (n == 0xFFFFFFFFu || fits_cap));
+            big |= on && !all && !unconstrained && qf >= 1048576.0f;
+            const u32 qr = all ? q_all : q;
+            cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
+        }
     }
     if (big) {                                  // rare: exact divisions
         cnt = cap;
@@ -573,8 +587,9 @@ struct ScanOut {
 // inclusive scan by shuffles, then every thread adds up the (few) warp totals below it serially — 8 loads
 // and adds beat a second 5-step shuffle scan on this latency-bound path.  The rank of a taker among the
 // workers that offer anything comes from a ballot, not from the scan.
+template <int MAXW>
 __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u32& parity, u32& seg_rank) {
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* buf = s_x + 32 * (parity & 1);
     parity++;
     u64 inc = cnt;
@@ -587,10 +602,11 @@ __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u
     if (lane == 31) buf[warp] = inc | ((u64)__popc(hasb) << 42);       // low 42 bits count, high bits offerers
     __syncthreads();
     u64 below = 0, all = 0;
-    for (u32 w2 = 0; w2 < nwarps; ++w2) {
+#pragma unroll
+    for (int w2 = 0; w2 < MAXW; ++w2) {          // slots of warps that do not exist stay zero (cleared at start)
         const u64 v = buf[w2];
         all += v;
-        if (w2 < warp) below += v;
+        below += (u32)w2 < warp ? v : 0ull;
     }
     const u64 mask = (1ull << 42) - 1;
     const u64 exc = (below & mask) + inc - cnt;
@@ -607,7 +623,7 @@ __device__ __forceinline__ ScanOut scan_take(u64 cnt, u32 remaining, u64* s_x, u
     return o;
 }
 
-template <int RT, bool SMALL, typename AT>
+template <int RT, int MAXT, bool SMALL, typename AT>
 __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     constexpr bool NARROW = sizeof(AT) == 4;
     constexpr AT AMAX = AmountMax<AT>::value;
@@ -623,6 +639,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     const u32 nwarps = blockDim.x >> 5;
     const bool has_worker = tid < a.W;
     u32 parity = 0;
+    if (tid < 64) s_x[tid] = 0;          // scan_take sums a fixed number of warp slots
 
     // ---- class table and variant order: in shared memory when they fit (SMALL: the pointers are then
     //      provably shared, so the sequential critical path uses LDS, not generic loads), else global
@@ -951,7 +968,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     FLUSH_SEGMENTS_IF_FULL();
                     const u64 cnt = has_worker ? __ldcg(a.pk.taken + (size_t)tid * PACK_MAX_CAND + cand_base + v) : 0;
                     u32 seg_rank;
-                    ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+                    ScanOut o = scan_take<MAXT / 32>(cnt, remaining, s_x, parity, seg_rank);
                     const Var& dv = classes[c].v[v];
                     if (o.take) {
                         const u32 si = seg_base + seg_rank;
@@ -1028,7 +1045,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                             take = (warp == wf && lane == first && can1) ? remaining : 0;
                             n_takers = 1; handed = remaining;
                         } else {
-                            ScanOut o = scan_take(cnt, remaining, s_x, parity, seg_rank);
+                            ScanOut o = scan_take<MAXT / 32>(cnt, remaining, s_x, parity, seg_rank);
                             take = o.take; exc_cnt = o.exc_cnt;
                             n_takers = (u32)__syncthreads_count(o.take != 0);
                             handed = (u32)(o.tot_cnt < remaining ? o.tot_cnt : remaining);
@@ -1141,7 +1158,7 @@ template <int RT, int MAXT, bool SMALL, typename AT>
 __global__ void __launch_bounds__(MAXT) solve_k(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     if (blockIdx.x == 0) {
-        solve_body<RT, SMALL, AT>(a, smem_dyn);
+        solve_body<RT, MAXT, SMALL, AT>(a, smem_dyn);
         return;
     }
     // ---- exclusive scan over chunks: one warp per group column, 32 chunk rows per step
@@ -1995,7 +2012,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                 const u64 amt = all ? 0 : sc.variants[v].amount[r] / gs[r];
                 if (amt > NARROW_LIMIT) narrow_ok = false;
                 amount[r] = (u32)amt;
-                rcp[r] = amt ? 1.0f / (float)(u32)amt : 0.0f;
+                rcp[r] = amt ? (1.0f / (float)(u32)amt) * (1.0f - 4.76837158203125e-7f) : 0.0f;   // biased low by 2^-21, see fit_count
                 rcp[RT + r] = all ? 0.0f : (float)(double)sc.variants[v].amount[r];
                 if (all || sc.variants[v].amount[r]) used |= 1u << r;
             }
