@@ -64,6 +64,22 @@ assert worker_dtype.itemsize == C.sizeof(hqs_worker) == 24
 assert assignment_dtype.itemsize == 8
 
 _lib = None
+_shim = None
+SHIM_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhqtako_shim.so")
+
+
+def load_shim() -> C.CDLL:
+    """Loads libhqtako_shim.so, the C++ host side above the C ABI (include/tako_shim.hpp).  Python only calls its
+    extern "C" self-test; C++ hosts link the library and use tako_b200::GpuCore directly."""
+    global _shim
+    if _shim is None:
+        load_library()
+        if not os.path.exists(SHIM_PATH):
+            raise LibraryNotBuilt(f"{SHIM_PATH} is missing: run `python __graft_entry__.py`")
+        _shim = C.CDLL(SHIM_PATH)
+        _shim.hqshim_selftest.argtypes = [C.c_int, C.c_int]
+        _shim.hqshim_selftest.restype = C.c_int
+    return _shim
 
 
 def load_library() -> C.CDLL:

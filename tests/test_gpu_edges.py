@@ -220,3 +220,10 @@ def test_large_amounts_with_a_common_factor_stay_narrow():
     wl = P.Workload(2, classes, total, total.copy(), rng.integers(0, 3, 5000).astype(np.uint32), rng.integers(0, 4, 5000).astype(np.int32))
     m = _check_exact(wl, expect_narrow=True)
     assert m.n_assigned() > 100
+
+
+def test_cpp_shim_selftest():
+    """tako_b200::GpuCore (C++ host side, include/tako_shim.hpp) through scenarios restated from test_scheduler_sn.rs
+    and a zero-duration drain with a host replay of every placement."""
+    from hyperqueue_b200 import _lib
+    assert _lib.load_shim().hqshim_selftest(0, 1) == 0
