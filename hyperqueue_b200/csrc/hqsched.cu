@@ -662,10 +662,12 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     }
     uint2* s_glist = reinterpret_cast<uint2*>(sp);
     u32* s_gcl = reinterpret_cast<u32*>(sp + (size_t)a.smem_glist_cap * sizeof(uint2));   // [gl_cap] class | level << 16
-    uint8_t* s_alive = sp + (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32));     // [gl_cap] group still placeable
+    u32* s_conf = reinterpret_cast<u32*>(sp + (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32)));   // bit e: group e confirmed placeable this round
+    const u32 n_conf_words = (a.smem_glist_cap + 31) / 32;
+    uint8_t* s_alive = reinterpret_cast<uint8_t*>(s_conf + n_conf_words);                 // [gl_cap] group still placeable
     // Outputs of the sequential loop are buffered in shared memory and written out in bulk: a global store
     // in front of a barrier costs an L2 round trip per step (bar.sync waits for the store to be visible).
-    unsigned char* sp2 = sp + (((size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1)) + 15 & ~size_t(15));
+    unsigned char* sp2 = sp + (((size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 2)) + 15 & ~size_t(15));
     GroupOut* s_gout = reinterpret_cast<GroupOut*>(sp2);                                   // [gl_cap], by entry
     u32* s_segc = reinterpret_cast<u32*>(sp2 + (size_t)a.smem_glist_cap * sizeof(GroupOut)); // [SEG_SMEM]
     u32* s_segw = s_segc + SEG_SMEM;
@@ -764,6 +766,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     const u32 n_list = s_nlist;
     for (u32 e = tid; e < gl_cap; e += blockDim.x) {
         s_alive[e] = 1;
+        if (e < n_conf_words) s_conf[e] = 0;
         GroupOut z; z.k = 0; z.out_off = 0; z.seg_lo = 0; z.seg_n = 0;
         s_gout[e] = z;
     }
@@ -861,12 +864,16 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     const u64 C = __shfl_sync(0xffffffffu, tot_v, r);
                     const u64 D = __shfl_sync(0xffffffffu, tot_v, RT + r);
                     if (C != HQS_AMOUNT_MAX && D > C) n_sat++;
-                    if (C != HQS_AMOUNT_MAX && D > 0) {
-                        const double x = __ddiv_rn(__ull2double_rn(C), __ull2double_rn(D));
-                        phi = x < phi ? x : phi;
-                    }
                 }
-                if (n_sat < 2) phi = 1.0;
+                if (n_sat >= 2)
+                    for (u32 r = 0; r < a.R; ++r) {
+                        const u64 C = __shfl_sync(0xffffffffu, tot_v, r);
+                        const u64 D = __shfl_sync(0xffffffffu, tot_v, RT + r);
+                        if (C != HQS_AMOUNT_MAX && D > 0) {
+                            const double x = __ddiv_rn(__ull2double_rn(C), __ull2double_rn(D));
+                            phi = x < phi ? x : phi;
+                        }
+                    }
                 const bool saturated = n_sat != 0;
                 if (saturated) {
                     // ---- a. quotas: share of each class proportional to how many fit on the worker alone
@@ -1113,11 +1120,12 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                         can = ok;
                     }
                 const u32 anyc = __ballot_sync(0xffffffffu, can);
-                if (lane == 0 && anyc) s_alive[e] = 2;                          // 2 = confirmed this round
+                if (lane == 0 && anyc) atomicOr(&s_conf[e >> 5], 1u << (e & 31));
             }
             __syncthreads();
-            for (u32 e = lj + tid; e < n_list; e += blockDim.x) s_alive[e] = s_alive[e] == 2 ? 1 : 0;
+            for (u32 e = lj + tid; e < n_list; e += blockDim.x) s_alive[e] = s_alive[e] && ((s_conf[e >> 5] >> (e & 31)) & 1);
             __syncthreads();
+            for (u32 i = tid; i < n_conf_words; i += blockDim.x) s_conf[i] = 0;      // next use is behind later barriers
         }
         t_groups += clock64() - t_l1;
         li = lj;
@@ -1822,7 +1830,7 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     size_t solve_smem = 0;
     if (a.smem_classes) solve_smem += ((a.classes_bytes + 15u) & ~15u) + ((ctx->Q * HQS_MAX_VARIANTS + 15u) & ~15u);
     a.smem_glist_cap = std::min<u32>(t.G, 2048);
-    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + 32;
+    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 2) + 32;
     solve_smem += (size_t)a.smem_glist_cap * sizeof(GroupOut) + 2 * SEG_SMEM * sizeof(u32);
     solve_smem = std::max(solve_smem, (size_t)nw * PACK_MAX_CAND * sizeof(double));     // pack warps' scratch
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));

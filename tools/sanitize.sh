@@ -7,6 +7,6 @@ T="tests/test_gpu_parity.py tests/test_gpu_edges.py"
 K="1000-8-6-2 or 4097-16-12-3 or narrow_amounts_with_remainders or eight_resources or indep3_2500_6_5_21"
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest $T -k "$K" -x -q 2>&1 | tail -6
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest $T -k "$K" -x -q 2>&1 | tail -30
   echo "rc=${PIPESTATUS[0]}"
 done
