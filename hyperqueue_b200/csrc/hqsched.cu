@@ -667,7 +667,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     uint8_t* s_alive = reinterpret_cast<uint8_t*>(s_conf + n_conf_words);                 // [gl_cap] group still placeable
     // Outputs of the sequential loop are buffered in shared memory and written out in bulk: a global store
     // in front of a barrier costs an L2 round trip per step (bar.sync waits for the store to be visible).
-    unsigned char* sp2 = sp + (((size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 2)) + 15 & ~size_t(15));
+    unsigned char* sp2 = sp + (((size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + (size_t)n_conf_words * 4 + 15) & ~size_t(15));
     GroupOut* s_gout = reinterpret_cast<GroupOut*>(sp2);                                   // [gl_cap], by entry
     u32* s_segc = reinterpret_cast<u32*>(sp2 + (size_t)a.smem_glist_cap * sizeof(GroupOut)); // [SEG_SMEM]
     u32* s_segw = s_segc + SEG_SMEM;
@@ -1830,7 +1830,7 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     size_t solve_smem = 0;
     if (a.smem_classes) solve_smem += ((a.classes_bytes + 15u) & ~15u) + ((ctx->Q * HQS_MAX_VARIANTS + 15u) & ~15u);
     a.smem_glist_cap = std::min<u32>(t.G, 2048);
-    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 2) + 32;
+    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + (size_t)((a.smem_glist_cap + 31) / 32) * 4 + 32;
     solve_smem += (size_t)a.smem_glist_cap * sizeof(GroupOut) + 2 * SEG_SMEM * sizeof(u32);
     solve_smem = std::max(solve_smem, (size_t)nw * PACK_MAX_CAND * sizeof(double));     // pack warps' scratch
     CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
