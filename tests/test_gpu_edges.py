@@ -227,3 +227,47 @@ def test_cpp_shim_selftest():
     and a zero-duration drain with a host replay of every placement."""
     from hyperqueue_b200 import _lib
     assert _lib.load_shim().hqshim_selftest(0, 1) == 0
+
+
+def _fuzz_workload(seed):
+    """Small random tick mixing everything the predicate knows: 1-6 resources, 1-4 variants, `All` entries, blocked
+    masks, time limits, partly used workers, amounts with and without a common factor."""
+    rng = np.random.default_rng(1000 + seed)
+    r = int(rng.integers(1, 7)); w = int(rng.integers(1, 41)); q = int(rng.integers(1, 9)); n = int(rng.integers(1, 1500))
+    unit = int(rng.choice([1, 2500, FR, 4 * FR]))                      # request granularity
+    classes, seen = [], set()
+    while len(classes) < q:
+        vs = []
+        for _ in range(int(rng.integers(1, 5))):
+            k = int(rng.integers(1, min(r, 3) + 1))
+            rs = [int(x) for x in rng.choice(r, size=k, replace=False)]
+            d = {"amounts": {x: int(rng.integers(1, 12)) * unit for x in rs}}
+            if r > 1 and rng.random() < 0.15:
+                allr = int(rng.choice([x for x in range(r) if x not in rs] or [rs[0]]))
+                if allr not in rs:
+                    d["all"] = (allr,)
+            if rng.random() < 0.2:
+                d["min_time_s"] = float(rng.choice([1.0, 30.0, 120.0]))
+            vs.append(d)
+        key = repr([(sorted(d["amounts"].items()), d.get("all"), d.get("min_time_s")) for d in vs])
+        if key not in seen:
+            seen.add(key); classes.append(vs)
+    total = rng.integers(4, 64, size=(w, r)).astype(np.uint64) * np.uint64(unit) + (
+        rng.integers(0, unit, size=(w, r)).astype(np.uint64) if rng.random() < 0.5 else np.uint64(0))
+    free = total.copy()
+    used = rng.random((w, r)) < 0.3
+    free[used] -= np.minimum(free[used], rng.integers(0, 20, size=int(used.sum())).astype(np.uint64) * np.uint64(unit))
+    blocked = None
+    if rng.random() < 0.4:
+        blocked = np.zeros((w, q, P.MAXV), dtype=bool)
+        blocked[:, :, :4] = rng.random((w, q, 4)) < 0.2
+    rem = None
+    if rng.random() < 0.4:
+        rem = np.where(rng.random(w) < 0.5, np.inf, rng.choice([0.5, 10.0, 60.0, 600.0], size=w))
+    return P.Workload(r, classes, total, free, rng.integers(0, q, n).astype(np.uint32), rng.integers(0, 5, n).astype(np.int32),
+                      blocked=blocked, worker_remaining_s=rem)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_ticks_match_specification(seed):
+    _check_exact(_fuzz_workload(seed))
