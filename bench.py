@@ -192,7 +192,12 @@ def run_cuda(args) -> None:
         s._check(lib.hqs_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
 
     def sharded_tick(s, bufs):
-        # count locally, all-gather the count vectors, replicated solve, local emit
+        if p2p:
+            # fused: count -> NVLink peer stores of the count vector + release flag -> the solver acquires the
+            # flags and sums the vectors on the device -> local emit.  No host collective on the data path.
+            s._check(lib.hqs_shard_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
+            return
+        # count locally, all-gather the count vectors (NCCL), replicated solve, local emit
         cnt, gathered = bufs
         ng = C.c_uint32(0)
         s._check(lib.hqs_shard_count(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None,
@@ -205,6 +210,13 @@ def run_cuda(args) -> None:
         s._sh = (allc, before)
         s._check(lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(allc.data_ptr()), C.c_void_p(before.data_ptr()), N_TASKS))
 
+    p2p = world > 1 and not args.nccl_exchange
+    if p2p:
+        from hyperqueue_b200.sharded import attach_peers
+        for s in scheds:
+            attach_peers(s, rank, world)
+            s._check(lib.hqs_tick_reserve(s._ctx, N_WORKERS, N_TASKS, 0))
+        dist.barrier()
     bufs = None
     if world > 1:
         with torch.cuda.stream(stream):
@@ -246,7 +258,7 @@ def run_cuda(args) -> None:
     barrier()
     t_host = time.perf_counter() - t_host0
     ms_total = ev0.elapsed_time(ev1)
-    launches_timed = 3 * K
+    launches_timed = (4 if p2p else 3) * K            # count_k, (xchg_k,) solve_k, emit_k per step
     # every step must have assigned every task
     for i in range(K):
         s = scheds[Wm + i]
@@ -336,8 +348,9 @@ def run_cuda(args) -> None:
         s2.close()
 
     # ---- e2e: host buffers through the public C ABI -----------------------------------------------
+    #      every step: this rank's tasks host -> device (hqs_ready_push), the tick, its assignments device -> host
     e2e = None
-    if rank == 0:
+    if world == 1 or p2p:
         s = scheds[0]
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
         h_handles, h_cls, h_prio = pin(handles), pin(np.ascontiguousarray(wl.task_class)), pin(prio)
@@ -347,21 +360,33 @@ def run_cuda(args) -> None:
 
         def e2e_step():
             s._check(lib.hqs_ready_push(s._ctx, N_TASKS, L.ptr(h_handles), L.ptr(h_cls), L.ptr(h_prio)))
-            s._check(lib.hqs_tick(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS,
-                                  L.ptr(out), C.byref(out_n), L.ptr(free_after)))
-            assert out_n.value == N_TASKS
+            if world == 1:
+                s._check(lib.hqs_tick(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS,
+                                      L.ptr(out), C.byref(out_n), L.ptr(free_after)))
+                assert out_n.value == N_TASKS
+            else:
+                s._check(lib.hqs_shard_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
+                s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(out), C.byref(out_n), L.ptr(free_after)))
         for _ in range(3):
             e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             e2e_step()
-        torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": N_TASKS / dt, "unit": "assignments/s", "ms_per_step": dt * 1000.0, "steps": n_e2e,
-               "h2d_bytes_per_step": int(N_TASKS * 16 + free.nbytes + total.nbytes + workers.nbytes),
-               "d2h_bytes_per_step": int(N_TASKS * 8 + free.nbytes + 16), "n_gpus": 1,
-               "note": "hqs_ready_push + hqs_tick with pinned host buffers, host clock around synchronised calls"}
+        n_step = N_TASKS
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            nn = torch.tensor([int(out_n.value)], dtype=torch.int64, device=dev)
+            dist.all_reduce(nn)
+            n_step = int(nn.item())
+        e2e = {"value": n_step / dt, "unit": "assignments/s", "ms_per_step": dt * 1000.0, "steps": n_e2e,
+               "h2d_bytes_per_step": int(world * (N_TASKS * 16 + free.nbytes + total.nbytes + workers.nbytes)),
+               "d2h_bytes_per_step": int(n_step * 8 + world * (free.nbytes + 16)), "n_gpus": world,
+               "note": "per rank: hqs_ready_push + tick + fetch with pinned host buffers; host clock between barriers, max over ranks"}
     clocks = sampler.stop()
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample --------------------------
@@ -398,6 +423,8 @@ def main() -> None:
     ap.add_argument("--ref-sample", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-drain", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="N > 1: all-gather the count vectors with NCCL instead of the fused peer-to-peer exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

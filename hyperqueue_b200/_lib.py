@@ -23,7 +23,9 @@ ABI_SYMBOLS = [
     "hqs_ready_remove", "hqs_dag_load", "hqs_tasks_finished", "hqs_tick", "hqs_tick_launch", "hqs_tick_fetch",
     "hqs_shard_count", "hqs_shard_solve_emit", "hqs_device_result", "hqs_ready_rearm", "hqs_stream", "hqs_sync",
     "hqs_get_stats", "hqs_set_stream", "hqs_set_profile", "hqs_get_kernel_ms", "hqs_debug_read", "hqs_levels_add", "hqs_query",
+    "hqs_shard_xbuf", "hqs_ipc_open", "hqs_shard_attach", "hqs_shard_tick_launch", "hqs_tick_reserve",
 ]
+HQS_IPC_HANDLE_BYTES = 64
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -108,6 +110,11 @@ def load_library() -> C.CDLL:
     lib.hqs_tick_fetch.argtypes = [vp, u32, vp, C.POINTER(C.c_uint32), u64p]
     lib.hqs_shard_count.argtypes = [vp, u32, vp, u64p, u64p, u8p, vp, u32, C.POINTER(C.c_uint32)]
     lib.hqs_shard_solve_emit.argtypes = [vp, vp, vp, u32]
+    lib.hqs_tick_reserve.argtypes = [vp, u32, u32, C.c_int]
+    lib.hqs_shard_xbuf.argtypes = [vp, C.POINTER(vp), vp]
+    lib.hqs_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.hqs_shard_attach.argtypes = [vp, u32, u32, C.POINTER(vp)]
+    lib.hqs_shard_tick_launch.argtypes = [vp, u32, vp, u64p, u64p, u8p, u32]
     lib.hqs_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.hqs_ready_rearm.argtypes = [vp]
     lib.hqs_stream.argtypes = [vp]

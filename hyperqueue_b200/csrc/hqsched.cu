@@ -227,6 +227,7 @@ constexpr u32 PACK_MAX_CAND = 64;    // (class, variant) candidates of the packe
 constexpr u32 PACK_MAX_ITER = 64;
 constexpr u32 PACK_CHUNK_DIV = 8;
 constexpr u32 PHASE_WAIT = 0, PHASE_PACK = 1, PHASE_EXIT = 2;
+constexpr u32 HQS_MAX_PEERS = 16;      // ranks of a sharded ready set
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000ll;   // ~2 s: a stuck grid must not hang the GPU
 
 // Amounts come in two widths.  u64: the ABI's fixed-point fractions as they are.  u32 ("narrow"): the same
@@ -294,6 +295,12 @@ struct SolveArgs {
     u64* free_after;         // [W][R]
     TickHeaderOut* hdr;
     uint2* glist;            // [G] scratch: non-empty groups (g, count) in processing order
+    // peer-to-peer count exchange (sharded tick without a host collective): x_world == 0 => off
+    const u32* x_counts;     // [x_world][HQS_MAX_GROUPS] count vectors written by the peers into MY exchange buffer
+    const u32* x_flags;      // [x_world] tick sequence number each peer stores after its vector
+    u32* x_all;              // [G] out: sum over ranks            (== total_all)
+    u32* x_before;           // [G] out: sum over lower ranks      (== before)
+    u32 x_world, x_rank, x_seq;
     // scan part
     u32* table;              // [P][G]
     u32 P;
@@ -310,6 +317,35 @@ __device__ __forceinline__ u32 ld_acquire(const u32* p) {
 }
 __device__ __forceinline__ void st_release(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sharded tick, exchange step: block r stores this rank's per-group counts into peer r's exchange buffer (NVLink
+// peer stores; r == own rank is a local copy) and then publishes the tick's sequence number with release
+// semantics at system scope.  The peer's solver acquires the flag before it reads the vector.
+struct XchgArgs {
+    u32* peer[HQS_MAX_PEERS];     // base of every rank's exchange buffer (own included)
+    u32 world, rank, seq, G;
+};
+__global__ void xchg_k(const u32* __restrict__ counts, XchgArgs x) {
+    const u32 r = blockIdx.x;
+    const u32 parity = x.seq & 1u;
+    u32* dst = x.peer[r] + ((size_t)parity * HQS_MAX_PEERS + x.rank) * HQS_MAX_GROUPS;
+    for (u32 g = threadIdx.x; g < x.G; g += blockDim.x) dst[g] = counts[g];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32* flags = x.peer[r] + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
+        st_release_sys(flags + x.rank, x.seq);
+    }
 }
 
 template <int RT, typename AT>
@@ -640,6 +676,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     const bool has_worker = tid < a.W;
     u32 parity = 0;
     if (tid < 64) s_x[tid] = 0;          // scan_take sums a fixed number of warp slots
+    if (tid < 40) s_b[tid] = 0;
 
     // ---- class table and variant order: in shared memory when they fit (SMALL: the pointers are then
     //      provably shared, so the sequential critical path uses LDS, not generic loads), else global
@@ -677,6 +714,32 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
 #define GC(e) ((e) < gl_cap ? (s_gcl[(e)] & 0xFFFFu) : (a.glist[(e)].x % a.Q))      /* class of entry e */
 #define GLV(e) ((e) < gl_cap ? (s_gcl[(e)] >> 16) : (a.glist[(e)].x / a.Q))        /* level of entry e */
 
+    bool x_timeout = false;
+    if (a.x_world) {
+        __syncthreads();
+        // sharded tick: wait until every rank's count vector of THIS tick has landed in my exchange buffer, then
+        // materialise sum-over-ranks and sum-over-lower-ranks (the two vectors the host all-gather used to provide)
+        if (tid < a.x_world) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(a.x_flags + tid) != a.x_seq) {
+                if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { s_b[1] = 1; break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        for (u32 g = tid; g < a.G; g += blockDim.x) {
+            u32 all = 0, bef = 0;
+            for (u32 r = 0; r < a.x_world; ++r) {
+                const u32 v = __ldcg(a.x_counts + (size_t)r * HQS_MAX_GROUPS + g);     // peers wrote it: bypass L1
+                all += v;
+                bef += r < a.x_rank ? v : 0u;
+            }
+            a.x_all[g] = all;
+            a.x_before[g] = bef;
+        }
+        __syncthreads();
+        x_timeout = s_b[1] == 1;
+    }
     const long long t_start = clock64();
     long long t_sat = 0, t_groups = 0;
     // worker state in registers.  Narrow path: fr/tot hold floor(amount / gscale[r]), `rem` what the division
@@ -1150,7 +1213,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
         a.hdr->n_assigned = out_base;
         a.hdr->n_groups = n_list;
         a.hdr->n_segments = seg_base;
-        a.hdr->error = sync_timeout ? 2u : (seg_overflow ? 1u : 0u);
+        a.hdr->error = (sync_timeout || x_timeout) ? 2u : (seg_overflow ? 1u : 0u);
         a.hdr->dbg[0] = t_compact - t_start; a.hdr->dbg[1] = t_sat; a.hdr->dbg[2] = t_groups;
         a.hdr->dbg[3] = t_loop - t_start; a.hdr->dbg[4] = n_list;
     }
@@ -1393,6 +1456,14 @@ struct hqs_ctx {
     u64 gscale[HQS_MAX_RESOURCES] = {};   // per-resource gcd of every requested amount (1 where nothing is requested)
     u64 narrow_limit[HQS_MAX_RESOURCES] = {};   // largest worker amount the narrow path can hold: gscale * (2^31 - 1)
     bool narrow_classes = false;          // every scaled class amount < 2^31
+    // peer-to-peer sharded tick
+    u32* d_xbuf = nullptr;                // my exchange buffer: [2][HQS_MAX_PEERS][HQS_MAX_GROUPS] counts + [2][HQS_MAX_PEERS] flags
+    u32* x_peer[HQS_MAX_PEERS] = {};      // every rank's exchange buffer (own included), set by hqs_shard_attach
+    std::vector<void*> x_opened;          // IPC mappings to close
+    u32 x_world = 0, x_rank = 0, x_seq = 0;
+    u32* d_xall = nullptr;                // [HQS_MAX_GROUPS] sum over ranks, written by the solver
+    u32* d_xbefore = nullptr;             // [HQS_MAX_GROUPS] sum over lower ranks
+    bool x_tick = false;                  // the tick being launched uses the exchange
     bool tick_narrow = false;             // this tick runs the narrow solver
     bool force_wide = false;              // hqs_create flag bit 1: always the 64-bit solver (tests)
     u32 RT = 4;                           // resource slots of the device class layout (4, 8 or 16)
@@ -1811,6 +1882,14 @@ int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& 
     a.hdr = ctx->d_hdr;
     a.glist = ctx->d_glist;
     a.table = ctx->d_table; a.P = t.P;
+    a.x_world = 0; a.x_rank = 0; a.x_seq = 0; a.x_counts = nullptr; a.x_flags = nullptr; a.x_all = nullptr; a.x_before = nullptr;
+    if (ctx->x_tick) {
+        const u32 parity = ctx->x_seq & 1u;
+        a.x_world = ctx->x_world; a.x_rank = ctx->x_rank; a.x_seq = ctx->x_seq;
+        a.x_counts = ctx->d_xbuf + (size_t)parity * HQS_MAX_PEERS * HQS_MAX_GROUPS;
+        a.x_flags = ctx->d_xbuf + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
+        a.x_all = ctx->d_xall; a.x_before = ctx->d_xbefore;
+    }
     a.sync = ctx->d_sync;
     a.pk.fr = ctx->d_pk_fr; a.pk.quota = ctx->d_pk_quota; a.pk.taken = ctx->d_pk_taken;
     a.pk.cand = ctx->d_pk_cand; a.pk.meta = ctx->d_pk_meta;
@@ -1931,6 +2010,10 @@ void hqs_destroy(hqs_ctx* ctx) {
                         ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
                         ctx->d_pk_quota, ctx->d_pk_taken, ctx->d_pk_cand, ctx->d_pk_meta};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
+    for (void* p : ctx->x_opened) cudaIpcCloseMemHandle(p);
+    if (ctx->d_xbuf) cudaFree(ctx->d_xbuf);
+    if (ctx->d_xall) cudaFree(ctx->d_xall);
+    if (ctx->d_xbefore) cudaFree(ctx->d_xbefore);
     if (ctx->h_tickin) cudaFreeHost(ctx->h_tickin);
     if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -2370,6 +2453,109 @@ int hqs_shard_solve_emit(hqs_ctx* ctx, const uint32_t* d_counts_all, const uint3
     if (rc) return rc;
     const TickLayout lay = tick_layout(ctx->last_W, ctx->R, ctx->Q, ctx->h_small[8] != 0);
     return launch_solve_emit(ctx, t, ctx->last_W, lay, ctx->h_small[8] != 0, d_counts_all, d_ranks_before, out_cap);
+}
+
+int hqs_tick_reserve(hqs_ctx* ctx, uint32_t n_workers, uint32_t out_cap, int with_blocked) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n_workers == 0 || n_workers > HQS_MAX_WORKERS) return fail(ctx, HQS_E_LIMIT, "n_workers=%u outside 1..%u", n_workers, HQS_MAX_WORKERS);
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
+    int rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap);
+    if (rc) return rc;
+    const TickLayout lay = tick_layout(n_workers, ctx->R, ctx->Q, with_blocked != 0);
+    if (lay.bytes > ctx->tickin_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_tickin) CU(cudaFree(ctx->d_tickin));
+        if (ctx->h_tickin) CU(cudaFreeHost(ctx->h_tickin));
+        ctx->tickin_cap = lay.bytes * 2;
+        CU(cudaMalloc(&ctx->d_tickin, ctx->tickin_cap));
+        CU(cudaMallocHost(&ctx->h_tickin, ctx->tickin_cap));
+    }
+    if (!ctx->h_hdr) {
+        ctx->h_hdr_cap = sizeof(TickHeaderOut) + (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * 8;
+        CU(cudaMallocHost(&ctx->h_hdr, ctx->h_hdr_cap));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HQS_OK;
+}
+
+static size_t xbuf_bytes() { return ((size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + 2 * HQS_MAX_PEERS) * sizeof(u32); }
+
+int hqs_shard_xbuf(hqs_ctx* ctx, void** d_xbuf, uint8_t ipc_handle[HQS_IPC_HANDLE_BYTES]) {
+    if (!ctx) return HQS_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_xbuf) {
+        CU(cudaMalloc(&ctx->d_xbuf, xbuf_bytes()));
+        CU(cudaMemset(ctx->d_xbuf, 0, xbuf_bytes()));
+        CU(cudaMalloc(&ctx->d_xall, HQS_MAX_GROUPS * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_xbefore, HQS_MAX_GROUPS * sizeof(u32)));
+    }
+    if (d_xbuf) *d_xbuf = ctx->d_xbuf;
+    if (ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == HQS_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ctx->d_xbuf));
+        memcpy(ipc_handle, &h, sizeof h);
+    }
+    return HQS_OK;
+}
+
+int hqs_ipc_open(hqs_ctx* ctx, const uint8_t ipc_handle[HQS_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!ctx || !ipc_handle || !d_ptr) return HQS_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->x_opened.push_back(p);
+    *d_ptr = p;
+    return HQS_OK;
+}
+
+int hqs_shard_attach(hqs_ctx* ctx, uint32_t world, uint32_t rank, void* const* peer_xbufs) {
+    if (!ctx || !peer_xbufs) return HQS_E_INVALID;
+    if (world < 1 || world > HQS_MAX_PEERS || rank >= world) return fail(ctx, HQS_E_LIMIT, "world=%u rank=%u outside 1..%u", world, rank, HQS_MAX_PEERS);
+    if (!ctx->d_xbuf) return fail(ctx, HQS_E_STATE, "hqs_shard_xbuf has not been called");
+    if (peer_xbufs[rank] != ctx->d_xbuf) return fail(ctx, HQS_E_INVALID, "peer_xbufs[rank] must be this context's own buffer");
+    for (u32 r = 0; r < world; ++r) {
+        if (!peer_xbufs[r]) return fail(ctx, HQS_E_INVALID, "peer %u has no buffer", r);
+        ctx->x_peer[r] = static_cast<u32*>(peer_xbufs[r]);
+    }
+    ctx->x_world = world; ctx->x_rank = rank; ctx->x_seq = 0;
+    return HQS_OK;
+}
+
+int hqs_shard_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+                          const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!ctx->x_world) return fail(ctx, HQS_E_STATE, "hqs_shard_attach has not been called");
+    int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const TickGeom t = tick_geom(ctx);
+    if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
+    if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap))) return rc;
+    TickLayout lay;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
+    if (ctx->n_handles) {
+        if ((rc = launch_count(ctx, t))) return rc;
+    } else {
+        CU(cudaMemsetAsync(ctx->d_total, 0, (size_t)t.G * 4, ctx->stream));
+    }
+    // every rank advances the sequence number in lockstep (one sharded tick = one exchange)
+    ctx->x_seq += 1;
+    XchgArgs x;
+    for (u32 r = 0; r < HQS_MAX_PEERS; ++r) x.peer[r] = r < ctx->x_world ? ctx->x_peer[r] : nullptr;
+    x.world = ctx->x_world; x.rank = ctx->x_rank; x.seq = ctx->x_seq; x.G = t.G;
+    xchg_k<<<ctx->x_world, 256, 0, ctx->stream>>>(ctx->d_total, x);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    ctx->x_tick = true;
+    rc = launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, ctx->d_xall, ctx->d_xbefore, out_cap);
+    ctx->x_tick = false;
+    return rc;
 }
 
 int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n) {

@@ -12,6 +12,12 @@ Per tick:
   4. the assignment lists are gathered where they are needed (host, or all-gather of (task, worker) pairs).
 No task data moves between GPUs.  The exchange logic is device-agnostic torch code so that it is covered
 by world_size-2 gloo tests on CPU (tests/test_sharded_cpu.py).
+
+Fused form (`ShardedScheduler(..., p2p=True)`, the default on GPUs): steps 1-3 are ONE stream of kernels with no
+host collective in between — the counting step's vector goes to every peer by NVLink peer stores (CUDA IPC
+mapped exchange buffers, hqs_shard_xbuf / hqs_ipc_open / hqs_shard_attach) followed by a release flag, and the
+solver kernel acquires all flags and sums the vectors itself (hqs_shard_tick_launch).  torch.distributed is then
+used once, at set-up, to pass the 64-byte IPC handles around.
 """
 from __future__ import annotations
 
@@ -38,6 +44,33 @@ def shard_exchange(counts_local: torch.Tensor, rank: int, world: int,
     return counts_all, before
 
 
+def attach_peers(sched, rank: int, world: int, group: Optional[dist.ProcessGroup] = None) -> None:
+    """One-time set-up of the peer-to-peer count exchange: every rank allocates its exchange buffer, the CUDA IPC
+    handles are all-gathered (64 bytes per rank, on the host), every rank maps the others' buffers."""
+    lib = sched._lib
+    own = C.c_void_p()
+    handle = (C.c_uint8 * L.HQS_IPC_HANDLE_BYTES)()
+    sched._check(lib.hqs_shard_xbuf(sched._ctx, C.byref(own), handle))
+    ptrs = (C.c_void_p * world)()
+    if world == 1:
+        ptrs[0] = own
+    else:
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8)
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        gathered = [torch.zeros(L.HQS_IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, mine.to(dev), group=group)
+        for r in range(world):
+            if r == rank:
+                ptrs[r] = own
+                continue
+            hb = (C.c_uint8 * L.HQS_IPC_HANDLE_BYTES)(*gathered[r].cpu().tolist())
+            p = C.c_void_p()
+            sched._check(lib.hqs_ipc_open(sched._ctx, hb, C.byref(p)))
+            ptrs[r] = p
+    sched._check(lib.hqs_shard_attach(sched._ctx, world, rank, ptrs))
+
+
 def block_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous handle range [lo, hi) of a rank; ranks are ordered by handle so that lower ranks hold the
     lower (earlier TaskId) handles — the global rank of a task inside its group needs exactly that."""
@@ -50,12 +83,15 @@ class ShardedScheduler:
     """Wraps one GpuScheduler per rank.  Handles given to / returned from this class are GLOBAL."""
 
     def __init__(self, sched, rank: int, world: int, n_total: int, device: torch.device,
-                 group: Optional[dist.ProcessGroup] = None) -> None:
+                 group: Optional[dist.ProcessGroup] = None, p2p: bool = False) -> None:
         self.s = sched
         self.rank, self.world, self.group = rank, world, group
         self.lo, self.hi = block_range(n_total, rank, world)
         self.device = device
         self._counts = torch.zeros(L.HQS_MAX_GROUPS, dtype=torch.int32, device=device)
+        self.p2p = bool(p2p)
+        if self.p2p:
+            attach_peers(sched, rank, world, group)
 
     def add_ready_tasks(self, handles, rq_ids, priorities) -> None:
         h = np.asarray(handles, dtype=np.int64)
@@ -74,6 +110,18 @@ class ShardedScheduler:
         free = np.ascontiguousarray(s.free)
         total = np.ascontiguousarray(s.total)
         blocked = s._blocked_bytes()
+        if self.p2p:
+            cap = out_cap or max(self.hi - self.lo, 1)
+            s._check(s._lib.hqs_shard_tick_launch(s._ctx, w.shape[0], L.ptr(w), L.ptr(free), L.ptr(total),
+                                                  L.ptr(blocked) if blocked is not None else None, cap))
+            out = np.zeros(cap, dtype=L.assignment_dtype)
+            free_after = np.zeros_like(free)
+            n = C.c_uint32(0)
+            s._check(s._lib.hqs_tick_fetch(s._ctx, cap, L.ptr(out), C.byref(n), L.ptr(free_after)))
+            a = out[: n.value].copy()
+            a["task"] += np.uint32(self.lo)
+            s.free = free_after
+            return a, free_after
         ng = C.c_uint32(0)
         s._check(s._lib.hqs_shard_count(s._ctx, w.shape[0], L.ptr(w), L.ptr(free), L.ptr(total),
                                         L.ptr(blocked) if blocked is not None else None,

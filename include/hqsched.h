@@ -183,6 +183,26 @@ int hqs_shard_count(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
                     uint32_t* d_counts, uint32_t n_groups_cap, uint32_t* n_groups);
 int hqs_shard_solve_emit(hqs_ctx* ctx, const uint32_t* d_counts_all, const uint32_t* d_ranks_before,
                          uint32_t out_cap);
+/* Allocates every buffer a tick over n_workers workers and up to out_cap assignments needs (they are otherwise
+ * allocated by the first tick).  cudaMalloc synchronises the device, so contexts that wait for each other on the
+ * device (the peer exchange below, several contexts of one process) reserve before their first tick. */
+int hqs_tick_reserve(hqs_ctx* ctx, uint32_t n_workers, uint32_t out_cap, int with_blocked);
+
+/* Sharded tick WITHOUT a host collective: the count vectors travel by peer-to-peer stores (NVLink) straight from
+ * the counting step into every rank's exchange buffer and the solver kernel waits for them on the device.
+ *   hqs_shard_xbuf     allocates this context's exchange buffer; returns its device pointer and its CUDA IPC handle
+ *   hqs_ipc_open       maps another process's exchange buffer (handle from its hqs_shard_xbuf) into this process
+ *   hqs_shard_attach   peer_xbufs[r] = exchange buffer of rank r as seen from this process (own buffer at [rank];
+ *                      contexts of one process pass each other's pointers directly)
+ *   hqs_shard_tick_launch = hqs_tick_launch for rank `rank` of `world`: count -> peer stores + release flag ->
+ *                      solve (acquires all flags, sums the vectors; same deterministic solve on every rank) ->
+ *                      emit of this rank's tasks.  Fetch with hqs_tick_fetch.  All ranks must tick in lockstep. */
+#define HQS_IPC_HANDLE_BYTES 64
+int hqs_shard_xbuf(hqs_ctx* ctx, void** d_xbuf, uint8_t ipc_handle[HQS_IPC_HANDLE_BYTES]);
+int hqs_ipc_open(hqs_ctx* ctx, const uint8_t ipc_handle[HQS_IPC_HANDLE_BYTES], void** d_ptr);
+int hqs_shard_attach(hqs_ctx* ctx, uint32_t world, uint32_t rank, void* const* peer_xbufs);
+int hqs_shard_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const uint64_t* free_rw,
+                          const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap);
 /* Device pointer / length of the last tick's assignment buffer (for NCCL all-gather of results). */
 int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n);
 
