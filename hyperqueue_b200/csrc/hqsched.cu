@@ -2519,9 +2519,18 @@ int hqs_shard_attach(hqs_ctx* ctx, uint32_t world, uint32_t rank, void* const* p
     if (world < 1 || world > HQS_MAX_PEERS || rank >= world) return fail(ctx, HQS_E_LIMIT, "world=%u rank=%u outside 1..%u", world, rank, HQS_MAX_PEERS);
     if (!ctx->d_xbuf) return fail(ctx, HQS_E_STATE, "hqs_shard_xbuf has not been called");
     if (peer_xbufs[rank] != ctx->d_xbuf) return fail(ctx, HQS_E_INVALID, "peer_xbufs[rank] must be this context's own buffer");
+    CU(cudaSetDevice(ctx->device));
     for (u32 r = 0; r < world; ++r) {
         if (!peer_xbufs[r]) return fail(ctx, HQS_E_INVALID, "peer %u has no buffer", r);
         ctx->x_peer[r] = static_cast<u32*>(peer_xbufs[r]);
+        // a buffer of another device of THIS process needs peer access (IPC mappings were opened with it)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, peer_xbufs[r]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != ctx->device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(ctx, HQS_E_CUDA, "no peer access from device %d to device %d: %s", ctx->device, at.device, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
     }
     ctx->x_world = world; ctx->x_rank = rank; ctx->x_seq = 0;
     return HQS_OK;
