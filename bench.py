@@ -165,7 +165,9 @@ def run_cuda(args) -> None:
 
     # one stream shared by every context so the ticks serialise and torch events time them
     stream = torch.cuda.Stream(device=dev)
-    wl = make_workload(N_TASKS, seed=0)        # one class table / worker pool for every rank
+    # one class table / worker pool for every rank; M1 = "every ready task is assignable in one tick", so the pool's
+    # free capacity grows with the number of ranks (weak scaling: 1 M tasks per GPU against world x the capacity)
+    wl = make_workload(N_TASKS, seed=0, free_scale=FREE_SCALE * world * int(os.environ.get("HQS_BENCH_POOL_MULT", "1")))
     if rank:
         wl.task_class = np.roll(wl.task_class, rank * 104729)
         wl.task_user_priority = np.roll(wl.task_user_priority, rank * 15485863 % N_TASKS)
@@ -402,7 +404,7 @@ def run_cuda(args) -> None:
             "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tasks_per_gpu": N_TASKS, "l2_policy": "each timed step runs on a different "
+            "config": {"workload": WORKLOAD, "tasks_per_gpu": N_TASKS, "pool_free_scale": FREE_SCALE * world, "all_assigned": bool(n_per_step == world * N_TASKS), "exchange": ("p2p" if p2p else ("nccl" if world > 1 else "none")), "l2_policy": "each timed step runs on a different "
                        "12 MB task table (K+W tables, 21 x 12 MB > 126 MB L2): inputs larger than L2",
                        "host_wall_ms_per_step": 1000.0 * t_host / K},
             "gpu_launches": launches_timed, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,

@@ -670,6 +670,7 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
     __shared__ u64 s_totmax[RT];
     __shared__ u32 s_a[40], s_b[40];
     __shared__ u32 s_nlist;
+    __shared__ u64 s_qsum[PACK_MAX_CAND * (MAXT / 32)];     // packed level: warp sums of the per-worker fit counts
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31, warp = tid >> 5;
     const u32 nwarps = blockDim.x >> 5;
@@ -939,29 +940,36 @@ __device__ void solve_body(const SolveArgs& a, unsigned char* smem_dyn) {
                     }
                 const bool saturated = n_sat != 0;
                 if (saturated) {
-                    // ---- a. quotas: share of each class proportional to how many fit on the worker alone
+                    // ---- a. quotas: share of each class proportional to how many fit on the worker alone.
+                    //      Pass 1: every worker's own count per group (stashed in its quota slot) and the warp
+                    //      sums; ONE barrier; pass 2: pool totals and the quotas.
+                    constexpr u32 NW = MAXT / 32;
                     for (u32 e = li; e < lj; ++e) {
                         const uint2 ge = GL(e);
                         const u32 c = GC(e), n = ge.y;
                         const uint8_t blk = (has_worker && a.blocked) ? a.blocked[(size_t)tid * a.Q + c] : 0;
                         u64 cn = 0;
-                        if (has_worker)
+                        if (has_worker) {
                             for (u32 v = 0; v < classes[c].n_variants; ++v) {
                                 const Var& dv = classes[c].v[v];
                                 if (!admissible(dv, v, blk, rem_time)) continue;
                                 const u64 f = fit_count<RT>(fr, tot, allok, dv, n);
                                 cn = f > cn ? f : cn;
                             }
+                            a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)] = (u32)cn;       // cn <= n < 2^32
+                        }
                         u64 x = cn;
 #pragma unroll
                         for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                        u64* buf = s_x + 32 * (parity & 1);
-                        parity++;
-                        if (lane == 0) buf[warp] = x;
-                        __syncthreads();
+                        if (lane == 0) s_qsum[(e - li) * NW + warp] = x;
+                    }
+                    __syncthreads();
+                    for (u32 e = li; e < lj; ++e) {
+                        const u32 n = GL(e).y;
                         u64 T = 0;
-                        for (u32 w2 = 0; w2 < nwarps; ++w2) T += buf[w2];
+                        for (u32 w2 = 0; w2 < nwarps; ++w2) T += s_qsum[(e - li) * NW + w2];
                         if (has_worker) {
+                            const u64 cn = a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)];   // this thread's own store
                             const u64 q = T ? ((u64)n * cn + T - 1) / T : 0;
                             const u64 q_phi = __double2ull_ru(__dmul_rn(__ull2double_rn(q), phi));     // ceil(q * phi)
                             a.pk.quota[(size_t)tid * PACK_MAX_CAND + (e - li)] = (u32)q_phi;
@@ -1987,8 +1995,15 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
             HQS_ALL(4, u64), HQS_ALL(8, u64), HQS_ALL(16, u64), HQS_ALL(4, u32), HQS_ALL(8, u32), HQS_ALL(16, u32)
 #undef HQS_ALL
         };
-        for (const void* f : fns)
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        // dynamic + static shared memory of a CTA may not exceed 227 KB: allow each instance what its statics leave
+        for (const void* f : fns) {
+            cudaFuncAttributes fa;
+            if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, f);
+            if (e == cudaSuccess) {
+                const size_t room = 227 * 1024 - fa.sharedSizeBytes;
+                e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(room, 200 * 1024));
+            }
+        }
     }
     if (e != cudaSuccess) {
         fail(nullptr, HQS_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));

@@ -96,3 +96,16 @@ def test_cpp_shim_builds_and_exports_the_reference_interface(lib):
     if not torch.cuda.is_available():
         # no device: the shim fails loudly (exception caught by the self-test => one failed check), no CPU path
         assert shim.hqshim_selftest(0, 0) >= 1
+
+
+def test_solver_shared_memory_budget(lib):
+    """Every solver instance must leave room for its worst-case dynamic shared memory (class table <= 48 KB, 2048
+    buffered groups, 4096 buffered segments: ~140 KB) inside the 227 KB a CTA may use — otherwise context set-up
+    fails on the device, which the CPU-only box would not notice."""
+    import subprocess
+    from hyperqueue_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    statics = [int(m) for blk in re.findall(r"Function [^\n]*solve_k[^\n]*\n[^\n]*", out) for m in re.findall(r"SHARED:(\d+)", blk)]
+    assert len(statics) >= 24
+    worst_dynamic = 48 * 1024 + 2048 * (8 + 4 + 1 + 16) + 256 + 2 * 4096 * 4 + 64
+    assert max(statics) + worst_dynamic <= 227 * 1024, (max(statics), worst_dynamic)
