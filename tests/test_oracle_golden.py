@@ -706,3 +706,20 @@ def test_schedule_min_utilization3():
     rt = TestEnv(); ts = rt.new_tasks(4, TB().cpus(3).weight(2.0)); t2 = rt.new_task(TB().cpus_all())
     rt.new_worker(WB(12).min_utilization(1.0)); rt.schedule()
     assert rt.n_assigned(ts) == 4 and not rt.task(t2).is_assigned()
+
+
+def test_schedule_mapping_do_not_change():
+    """test_scheduler_mapping.rs:16-44: a second tick emits nothing; a task whose only capable worker is busy stays
+    in the queue without disturbing the existing assignment."""
+    rt = TestEnv()
+    rt.new_named_resource("gpus")
+    w1 = rt.new_worker(WB(6).res_sum("gpus", 2))
+    rt.new_worker(WB(3))
+    t1 = rt.new_task(TB().cpus(5))
+    rt.schedule()
+    assert rt.task(t1).state == "assigned" and rt.task(t1).worker == w1
+    assert t1 in rt.worker(w1).assigned_tasks
+    assert not rt.schedule().workers
+    rt.new_worker(WB(6))
+    rt.new_task(TB().cpus(4).add_resource(1, 2))
+    assert not rt.schedule().workers
