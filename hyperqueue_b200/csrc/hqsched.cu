@@ -17,10 +17,17 @@
 //   deps[h]  u32  unfinished dependencies (DAG mode), cons_off/cons: CSR of consumers
 // One tick = 3 kernels on one stream:
 //   count_k : per-chunk histogram of ready tasks by group g = level*Q + class   (HBM streaming, 4 B/task)
-//   solve_k : CTA 0: sequential first-fit over non-empty groups, one thread per worker;
-//             CTAs 1..: exclusive scan of the per-chunk histograms over chunks (runs concurrently)
+//   solve_k : CTA 0: sequential first-fit over non-empty groups, one thread per worker (worker state in
+//             registers; amounts gcd-scaled to 32 bits when the tick allows it, else 64-bit);
+//             CTAs 1..: exclusive scan of the per-chunk histograms over chunks (runs concurrently), then they
+//             stand by: when CTA 0 finds the first saturated priority level it hands every worker to one warp
+//             of those CTAs, which fills it independently (pack_body) and reports back;
 //   emit_k  : stable rank of every ready task inside its group, rank -> (worker, variant) through
 //             the solver's count segments, compact write of 8-byte assignments, READY -> DONE
+// Sharded over several GPUs (one context per GPU, tasks block-sharded, workers replicated) a fourth kernel,
+// xchg_k, stores the rank's count vector into every peer's exchange buffer over NVLink between count_k and
+// solve_k; solve_k acquires the peers' flags and sums the vectors itself (no host collective).
+// The algorithm has a sequential specification, tests/greedy_model.py, which the kernels equal bit for bit.
 #include "../../include/hqsched.h"
 
 #include <cuda_runtime.h>
