@@ -147,6 +147,7 @@ def run_scheduling_solver(core, now: float, batches: Sequence[TaskBatch],
             bvars[key] = v
         return v
 
+    capable: Dict[Tuple[int, int], bool] = {}
     for b in batches:
         counts = count_vars.get(b.resource_rq_id)
         if counts is None:
@@ -164,7 +165,11 @@ def run_scheduling_solver(core, now: float, batches: Sequence[TaskBatch],
                 for w in workers:
                     if not w.is_sn():
                         continue
-                    if not w.is_capable_to_run_rqv(blocker_rqv, now):
+                    ck = (w.id, blocker_rq)
+                    cap = capable.get(ck)
+                    if cap is None:                       # pure in (worker, blocker) within one tick
+                        cap = capable[ck] = w.is_capable_to_run_rqv(blocker_rqv, now)
+                    if not cap:
                         continue
                     gap = core.scheduler_state.gap_cache.get_gap(
                         blocker_rq, b.resource_rq_id, w.resources,
