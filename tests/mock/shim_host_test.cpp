@@ -1,0 +1,97 @@
+// Host-logic checks of tako_b200::GpuCore against the test double of the C ABI (fake_hqsched.cpp): what the shim
+// does around a tick — interning, handle mapping, batched pushes, applying the result to its worker mirror,
+// min_utilization hand-back, resource return, worker removal.  Returns the number of failed checks.
+#include "../../include/tako_shim.hpp"
+
+#include <cstdio>
+#include <stdexcept>
+
+using namespace tako_b200;
+
+static int failed = 0;
+static void check(bool ok, const char* what) {
+    if (!ok) { ++failed; std::fprintf(stderr, "FAILED: %s\n", what); }
+}
+static ResourceRequestVariants cpus(uint64_t n) {
+    ResourceRequest rq;
+    rq.entries.push_back({0, false, n * FRACTIONS_PER_UNIT});
+    return ResourceRequestVariants{{rq}};
+}
+
+int main() {
+    {   // interning + per-worker priority order + free vectors + resource return
+        GpuCore core(2, 0);
+        const ResourceRqId c1 = core.get_or_create_resource_rq_id(cpus(1)), c2 = core.get_or_create_resource_rq_id(cpus(2));
+        check(core.get_or_create_resource_rq_id(cpus(1)) == c1 && c1 != c2, "interning");
+        ResourceRequestVariants all_gpu = cpus(1);
+        all_gpu.variants[0].entries.push_back({1, true, 0});
+        const ResourceRqId ca = core.get_or_create_resource_rq_id(all_gpu);
+        core.on_new_worker(7, {4 * FRACTIONS_PER_UNIT, 2 * FRACTIONS_PER_UNIT});
+        core.on_new_worker(3, {2 * FRACTIONS_PER_UNIT, 0});
+        core.add_ready_task(TaskId{1, 10}, c2, priority_from_user(1));
+        core.add_ready_task(TaskId{1, 11}, c1, priority_from_user(5));
+        core.add_ready_task(TaskId{1, 12}, ca, priority_from_user(3));
+        core.add_ready_task(TaskId{1, 13}, c2, priority_from_user(0));
+        check(core.stats().kernel_launches == 0, "pushes are batched until the tick");
+        WorkerTaskMapping m = core.run_scheduling();
+        check(core.stats().kernel_launches == 4, "one batched push of four tasks");
+        // first-fit in worker-id order: worker 3 (2 cpus) gets task 11 (prio 5); task 12 (All gpus) only fits worker 7;
+        // task 10 (2 cpus, prio 1) -> worker 7; task 13 (2 cpus) does not fit any more (worker 7 has 1 cpu left, worker 3 has 1)
+        check(m.n_assigned() == 3, "three of four tasks placed");
+        check(m.workers.count(3) && m.workers[3].assigned.size() == 1 && m.workers[3].assigned[0].first == (TaskId{1, 11}), "worker 3 list");
+        check(m.workers.count(7) && m.workers[7].assigned.size() == 2 && m.workers[7].assigned[0].first == (TaskId{1, 12}) &&
+              m.workers[7].assigned[1].first == (TaskId{1, 10}), "worker 7 list is priority-descending");
+        check(core.free_resources(7)[0] == 1 * FRACTIONS_PER_UNIT && core.free_resources(7)[1] == 0, "All consumed the whole resource");
+        core.on_task_finished(TaskId{1, 12});
+        check(core.free_resources(7)[0] == 2 * FRACTIONS_PER_UNIT && core.free_resources(7)[1] == 2 * FRACTIONS_PER_UNIT, "finish restores All to the total");
+        m = core.run_scheduling();
+        check(m.n_assigned() == 1 && m.workers[7].assigned[0].first == (TaskId{1, 13}), "the waiting task runs after resources return");
+        check(core.run_scheduling().n_assigned() == 0, "a second tick emits nothing");
+    }
+    {   // cancel before and after the flush, worker removal requeues its tasks
+        GpuCore core(1, 0);
+        const ResourceRqId c1 = core.get_or_create_resource_rq_id(cpus(1));
+        core.on_new_worker(1, {1 * FRACTIONS_PER_UNIT});
+        core.add_ready_task(TaskId{2, 1}, c1, priority_from_user(0));
+        core.add_ready_task(TaskId{2, 2}, c1, priority_from_user(0));
+        core.remove_ready_task(TaskId{2, 1});                          // still in the host batch
+        check(core.stats().n_segments == 0, "cancel of an unflushed task does not reach the library");
+        WorkerTaskMapping m = core.run_scheduling();
+        check(m.n_assigned() == 1 && m.workers[1].assigned[0].first == (TaskId{2, 2}), "cancelled task is never scheduled");
+        core.add_ready_task(TaskId{2, 3}, c1, priority_from_user(0));
+        check(core.run_scheduling().n_assigned() == 0, "no capacity left");
+        core.remove_ready_task(TaskId{2, 3});
+        check(core.stats().n_segments == 1, "cancel of a flushed task goes to hqs_ready_remove");
+        core.on_new_worker(2, {1 * FRACTIONS_PER_UNIT});
+        core.on_remove_worker(1);                                      // task {2,2} was running there
+        m = core.run_scheduling();
+        check(m.n_assigned() == 1 && m.workers.count(2) && m.workers[2].assigned[0].first == (TaskId{2, 2}), "tasks of a lost worker are rescheduled");
+    }
+    {   // min_utilization: 3-cpu tasks on a 12-cpu worker (test_schedule_min_utilization1, test_scheduler_sn.rs:1391-1414)
+        const struct { int n; float mu; size_t expect; } rows[] = {{2, 0.5f, 2}, {2, 0.51f, 0}, {3, 0.51f, 3}, {3, 0.75f, 3}, {3, 0.76f, 0}};
+        for (const auto& row : rows) {
+            GpuCore core(1, 0);
+            const ResourceRqId c3 = core.get_or_create_resource_rq_id(cpus(3));
+            core.on_new_worker(1, {12 * FRACTIONS_PER_UNIT}, row.mu);
+            for (int t = 0; t < row.n; ++t) core.add_ready_task(TaskId{3, (uint32_t)t}, c3, priority_from_user(0));
+            const WorkerTaskMapping m = core.run_scheduling();
+            check(m.n_assigned() == row.expect, "min_utilization: all or nothing");
+            if (row.expect == 0) {
+                check(core.free_resources(1)[0] == 12 * FRACTIONS_PER_UNIT, "dropped placements leave the worker untouched");
+                check(core.stats().kernel_launches == (uint64_t)2 * row.n, "dropped tasks are pushed back into the ready set");
+            }
+        }
+    }
+    {   // error behaviour: invalid requests throw, like the reference's panics
+        GpuCore core(1, 0);
+        bool threw = false;
+        try { ResourceRequest rq; rq.entries.push_back({0, false, 0}); core.get_or_create_resource_rq_id(ResourceRequestVariants{{rq}}); }
+        catch (const std::invalid_argument&) { threw = true; }
+        check(threw, "zero amount is refused");
+        threw = false;
+        try { core.add_ready_task(TaskId{9, 9}, 77, 0); } catch (const std::invalid_argument&) { threw = true; }
+        check(threw, "unknown request id is refused");
+    }
+    std::fprintf(stderr, "shim host test: %d failed\n", failed);
+    return failed;
+}
