@@ -58,10 +58,10 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "hyperqueue_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            src = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".cu", ".h", ".cpp", ".hpp")) else ""
+            src = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) else ""
             if f.endswith(".py"):
                 assert not re.search(r"^\s*(import|from)\s+(oracle|greedy_model|parity)\b", src, flags=re.M), f
-            if f.endswith((".cu", ".h", ".cpp", ".hpp")):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f
     so = os.path.join(pkg, "libhqsched_b200.so")
     out = __import__("subprocess").run(["ldd", so], capture_output=True, text=True).stdout

@@ -22,7 +22,7 @@ def test_the_double_is_not_part_of_the_product():
     pkg = os.path.join(ROOT, "hyperqueue_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 assert "fake_hqsched" not in open(os.path.join(dirpath, f), errors="ignore").read(), f
     assert "fake_hqsched" not in open(os.path.join(ROOT, "__graft_entry__.py")).read()
     assert "fake_hqsched" not in open(os.path.join(ROOT, "bench.py")).read()

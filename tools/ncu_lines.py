@@ -16,7 +16,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kregex, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 so = os.path.join(ROOT, "hyperqueue_b200", "libhqsched_b200.so")
-src = open(os.path.join(ROOT, "hyperqueue_b200", "csrc", "hqsched.cu")).read().split("\n")
+_src_cache = {}
+
+
+def src_line(path, line):
+    """Source text of (file, line); the kernels live in hqsched.cu and the .cuh files it includes."""
+    if path is None or line is None:
+        return ""
+    local = os.path.join(ROOT, "hyperqueue_b200", "csrc", os.path.basename(path))
+    if local not in _src_cache:
+        _src_cache[local] = open(local).read().split("\n") if os.path.exists(local) else []
+    lines = _src_cache[local]
+    return lines[line - 1].strip() if 0 < line <= len(lines) else ""
 
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=td, check=True, capture_output=True)
@@ -27,9 +38,9 @@ ins, cur = [], None
 for l in dis[start + 1:]:
     if l.startswith("//--------------------- "):
         break
-    m = re.search(r'//## File "[^"]+", line (\d+)', l)
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
-        cur = int(m.group(1))
+        cur = (m.group(1), int(m.group(2)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
@@ -53,4 +64,5 @@ tot_s = sum(v[1] for v in by.values())
 print(f"SASS instructions {len(ins)}, warp-instructions executed {tot_i}, samples {tot_s}")
 print("stalls:", sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
 for l, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:top]:
-    print(f"{l!s:>5} {v[0]:>9} {100.0 * v[0] / tot_i:5.1f}% {v[1]:>6}  {src[l - 1].strip()[:100] if l else ''}")
+    where = f"{os.path.basename(l[0])}:{l[1]}" if l else "?"
+    print(f"{where:>24} {v[0]:>9} {100.0 * v[0] / tot_i:5.1f}% {v[1]:>6}  {src_line(*l)[:100] if l else ''}")
