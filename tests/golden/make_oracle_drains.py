@@ -30,6 +30,10 @@ CASES = {
     "indep3_5000_16_10_11": ("indep", [5000, 16, 10, 11], {"variants3": True}),
     "indep_6000_10_10_13": ("indep", [6000, 10, 10, 13], {}),
     "indep3_2500_6_5_21": ("indep", [2500, 6, 5, 21], {"variants3": True}),
+    # second held-out batch: 5 % blocked (worker, class, variant) triples, a larger pool, another DAG
+    "indep3b_4000_12_8_31": ("indep", [4000, 12, 8, 31], {"variants3": True, "blocked_density": 0.05}),
+    "indep_10000_24_20_33": ("indep", [10000, 24, 20, 33], {}),
+    "dag_5000_10_8_35": ("dag", [5000, 10, 8, 35], {"window": 256}),
 }
 
 out = {}
