@@ -128,7 +128,7 @@ ALL_DRAINS = sorted(json.load(open(GOLDEN)).keys())
 @pytest.mark.parametrize("key", ALL_DRAINS)
 def test_drain_makespan_vs_oracle(key):
     """north_star: the zero-duration drain takes at most 2 % more ticks than the reference scheduler (finishing
-    earlier is fine).  Six cases were used while designing the packing rules, five (see make_oracle_drains.py)
+    earlier is fine).  Six cases were used while designing the packing rules, eight (see make_oracle_drains.py)
     were generated afterwards as held-out checks."""
     golden = json.load(open(GOLDEN))[key]
     wl = (P.make_dag if key.startswith("dag") else P.make_independent)(*golden["args"], **golden.get("kwargs", {}))
