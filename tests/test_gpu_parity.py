@@ -122,7 +122,7 @@ def test_many_priority_levels_are_coarsened_not_rejected():
 # ---------------------------------------------------------------------------------------------------
 # drain (mode M2): feasibility every tick, resources conserved, makespan
 # ---------------------------------------------------------------------------------------------------
-ALL_DRAINS = sorted(json.load(open(GOLDEN)).keys())
+ALL_DRAINS = sorted(k for k in json.load(open(GOLDEN)).keys() if not k.startswith("big_") or os.environ.get("HQS_BIG_DRAINS"))
 
 
 @pytest.mark.parametrize("key", ALL_DRAINS)
