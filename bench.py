@@ -214,10 +214,22 @@ def run_cuda(args) -> None:
 
     p2p = world > 1 and not args.nccl_exchange
     if p2p:
-        from hyperqueue_b200.sharded import attach_peers
-        for s in scheds:
-            attach_peers(s, rank, world)
-            s._check(lib.hqs_tick_reserve(s._ctx, N_WORKERS, N_TASKS, 0))
+        from hyperqueue_b200.sharded import gather_peer_handles, open_and_attach
+        ok = 1
+        try:
+            pending = [gather_peer_handles(s, rank, world) for s in scheds]      # collective: every rank, every context
+        except Exception as e:
+            raise SystemExit(f"[bench] exchange-buffer set-up failed on rank {rank}: {e}")
+        try:
+            for s, (own, handles) in zip(scheds, pending):                      # local: may fail without hanging the others
+                open_and_attach(s, rank, world, own, handles)
+                s._check(lib.hqs_tick_reserve(s._ctx, N_WORKERS, N_TASKS, 0))
+        except Exception as e:          # e.g. CUDA IPC not permitted in this container: every rank falls back together
+            print(f"[bench] rank {rank}: peer-to-peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        p2p = bool(flag.item())
         dist.barrier()
     bufs = None
     if world > 1:

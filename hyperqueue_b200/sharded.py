@@ -44,31 +44,43 @@ def shard_exchange(counts_local: torch.Tensor, rank: int, world: int,
     return counts_all, before
 
 
-def attach_peers(sched, rank: int, world: int, group: Optional[dist.ProcessGroup] = None) -> None:
-    """One-time set-up of the peer-to-peer count exchange: every rank allocates its exchange buffer, the CUDA IPC
-    handles are all-gathered (64 bytes per rank, on the host), every rank maps the others' buffers."""
+def gather_peer_handles(sched, rank: int, world: int, group: Optional[dist.ProcessGroup] = None):
+    """Collective half of the set-up: allocates this rank's exchange buffer and all-gathers the 64-byte CUDA IPC
+    handles (on the host).  Returns (own device pointer, [handle bytes of rank r])."""
     lib = sched._lib
     own = C.c_void_p()
     handle = (C.c_uint8 * L.HQS_IPC_HANDLE_BYTES)()
     sched._check(lib.hqs_shard_xbuf(sched._ctx, C.byref(own), handle))
-    ptrs = (C.c_void_p * world)()
     if world == 1:
-        ptrs[0] = own
-    else:
-        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8)
-        backend = dist.get_backend(group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        gathered = [torch.zeros(L.HQS_IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
-        dist.all_gather(gathered, mine.to(dev), group=group)
-        for r in range(world):
-            if r == rank:
-                ptrs[r] = own
-                continue
-            hb = (C.c_uint8 * L.HQS_IPC_HANDLE_BYTES)(*gathered[r].cpu().tolist())
-            p = C.c_void_p()
-            sched._check(lib.hqs_ipc_open(sched._ctx, hb, C.byref(p)))
-            ptrs[r] = p
+        return own, [bytes(handle)]
+    mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    gathered = [torch.zeros(L.HQS_IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, mine.to(dev), group=group)
+    return own, [bytes(g.cpu().tolist()) for g in gathered]
+
+
+def open_and_attach(sched, rank: int, world: int, own, handles) -> None:
+    """Local half: maps the other ranks' buffers (cudaIpcOpenMemHandle) and attaches the context."""
+    lib = sched._lib
+    ptrs = (C.c_void_p * world)()
+    for r in range(world):
+        if r == rank:
+            ptrs[r] = own
+            continue
+        hb = (C.c_uint8 * L.HQS_IPC_HANDLE_BYTES)(*handles[r])
+        p = C.c_void_p()
+        sched._check(lib.hqs_ipc_open(sched._ctx, hb, C.byref(p)))
+        ptrs[r] = p
     sched._check(lib.hqs_shard_attach(sched._ctx, world, rank, ptrs))
+
+
+def attach_peers(sched, rank: int, world: int, group: Optional[dist.ProcessGroup] = None) -> None:
+    """One-time set-up of the peer-to-peer count exchange: every rank allocates its exchange buffer, the CUDA IPC
+    handles are all-gathered (64 bytes per rank, on the host), every rank maps the others' buffers."""
+    own, handles = gather_peer_handles(sched, rank, world, group)
+    open_and_attach(sched, rank, world, own, handles)
 
 
 def block_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:

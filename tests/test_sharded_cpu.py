@@ -71,3 +71,64 @@ def test_block_ranges_cover_everything_in_order():
         rs = [block_range(n, r, w) for r in range(w)]
         assert rs[0][0] == 0 and rs[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+
+
+class _FakeLib:
+    """Stand-in for the three exchange set-up entry points: records what the Python plumbing passes around."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.opened = []
+        self.attached = None
+
+    def hqs_shard_xbuf(self, ctx, p_own, handle):
+        import ctypes as C
+        C.cast(p_own, C.POINTER(C.c_void_p))[0] = 0x1000 + self.rank
+        for i in range(64):
+            handle[i] = (self.rank * 37 + i) % 256
+        return 0
+
+    def hqs_ipc_open(self, ctx, handle, p_out):
+        import ctypes as C
+        hb = bytes(handle)
+        self.opened.append(hb)
+        C.cast(p_out, C.POINTER(C.c_void_p))[0] = 0x2000 + hb[0]
+        return 0
+
+    def hqs_shard_attach(self, ctx, world, rank, ptrs):
+        self.attached = (world, rank, [int(ptrs[r] or 0) for r in range(world)])
+        return 0
+
+
+class _FakeSched:
+    def __init__(self, rank):
+        self._lib, self._ctx = _FakeLib(rank), None
+
+    def _check(self, rc):
+        assert rc == 0
+
+
+def _attach_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hyperqueue_b200.sharded import attach_peers
+    s = _FakeSched(rank)
+    attach_peers(s, rank, world)
+    ret[rank] = (s._lib.opened, s._lib.attached)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_handle_exchange_plumbing():
+    """attach_peers: every rank must open exactly the other ranks' 64-byte handles, unmodified, and attach with its own
+    buffer at its own index (the device side of the exchange is covered on the GPU)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_attach_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        opened, attached = ret[rank]
+        other = 1 - rank
+        assert opened == [bytes((other * 37 + i) % 256 for i in range(64))]
+        assert attached[0] == world and attached[1] == rank
+        assert attached[2][rank] == 0x1000 + rank and attached[2][other] == 0x2000 + (other * 37) % 256
