@@ -17,7 +17,7 @@ from oracle import judge as J
 from oracle import model as M
 from oracle.core import Core, Task
 
-from workloads import (FR, MAXV, Workload, dag_csr, gpu_scheduler, make_dag, make_independent,  # noqa: F401
+from workloads import (FR, MAXV, Workload, dag_csr, gpu_scheduler, make_cfg1, make_dag, make_independent,  # noqa: F401
                        _class_pool, _zipf_classes)
 
 

@@ -112,6 +112,14 @@ def make_independent(n: int, w: int, q: int, seed: int = 0, free_scale: int = 1,
                     name=f"indep n={n} w={w} q={q} v={'3' if variants3 else '1'}")
 
 
+def make_cfg1(n: int = 10_000, w: int = 4) -> Workload:
+    """BASELINE.json configs[0]: n independent 1-cpu tasks, w workers x {cpus 128}, one class, priority 0 — the shape of
+    the reference's experiment-per-task-overhead.py."""
+    total = np.tile(np.array([128 * FR], dtype=np.uint64), (w, 1))
+    return Workload(1, [[{"amounts": {0: 1 * FR}}]], total, total.copy(), np.zeros(n, dtype=np.uint32),
+                    np.zeros(n, dtype=np.int32), name=f"cfg1 n={n} w={w}")
+
+
 def make_dag(n: int, w: int, q: int, seed: int = 0, window: int = 4096, max_deg: int = 8) -> Workload:
     """cfg4 shape: topological ids, in-degree U{0..8} from the previous `window` ids, out-degree <= 8 by
     rejection, unit b-level as user priority (the reference has no b-level: SURVEY.md §0)."""
