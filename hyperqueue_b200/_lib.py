@@ -13,6 +13,7 @@ HQS_MAX_CLASSES = 4096
 HQS_MAX_GROUPS = 4096
 HQS_AMOUNT_MAX = (1 << 64) - 1
 HQS_TIME_INF = (1 << 64) - 1
+HQS_CREATE_NO_PACK, HQS_CREATE_WIDE_AMOUNTS, HQS_CREATE_SHARE_DEVICE = 1, 2, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhqsched_b200.so")

@@ -1,4 +1,4 @@
-// hqs_ready_set.cuh — task-table key encoding, per-tick device records, ready-set maintenance kernels and count_k.
+// hqs_ready_set.cuh — task-table key encoding, per-tick device records and the ready-set maintenance kernels.
 // Included by hqsched.cu inside its anonymous namespace (one translation unit; see the header of hqsched.cu).
 #pragma once
 
@@ -9,8 +9,6 @@ constexpr u32 KEY_LEVEL_SHIFT = 14;
 constexpr u32 KEY_LEVEL_MASK = 0x7FFFu;
 constexpr u32 KEY_CLASS_MASK = 0x3FFFu;
 
-constexpr u32 COUNT_THREADS = 1024;       // count_k: one uint4 (4 tasks) per thread and pass
-constexpr u32 EMIT_SMEM_BUDGET = 96 * 1024;
 constexpr u32 SEG_CAP = 1u << 20;         // (group, worker, variant) count segments per tick
 constexpr u32 NEWPRIO_CAP = 4096;
 
@@ -29,8 +27,8 @@ struct TickHeaderOut {
     u32 n_assigned;  // local assignments
     u32 n_groups;
     u32 n_segments;
-    u32 error;       // 1 = segment overflow, 2 = solver grid synchronisation timed out
-    unsigned long long dbg[8];   // clock64 phase stamps of CTA 0 (debug)
+    u32 error;       // 1 = segment overflow, 2 = a grid wait timed out, 3 = out_cap too small (nothing was emitted)
+    unsigned long long dbg[8];   // clock64 phase lengths of the solver CTA (hqs_debug_read)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,44 +133,3 @@ __global__ void finished_k(u32 n, const u32* __restrict__ task, const u32* __res
     made = __reduce_add_sync(0xffffffffu, made);
     if ((threadIdx.x & 31) == 0 && made) atomicAdd(n_new, made);
 }
-
-// ------------------------------------------------------------------------------------------------
-// K1: count_k — histogram of ready tasks per group for one chunk of the task table.
-// HBM traffic: 4 B read per table slot.  smem: G u32 counters.  One uint4 (4 tasks) per thread.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-count_k(const u32* __restrict__ key, u32 n_handles, u32 chunk, u32 Q, u32 G, u32* __restrict__ table,
-        u32* __restrict__ total) {
-    extern __shared__ u32 s_hist[];
-    for (u32 g = threadIdx.x; g < G; g += blockDim.x) s_hist[g] = 0;
-    __syncthreads();
-    const u32 base = blockIdx.x * chunk;
-    const u32 end = min(base + chunk, n_handles);
-    // chunk and base are multiples of 256 => 16-byte aligned uint4 loads; a ragged tail is scalar.
-    const u32 vec_end = base + ((end - base) & ~3u);
-    for (u32 rowb = base; rowb < end; rowb += blockDim.x * 4) {
-        const u32 i = rowb + threadIdx.x * 4;
-        u32 k[4];
-        if (i + 4 <= vec_end) {
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(key + i));
-            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) k[j] = (i + j < end) ? __ldg(key + i + j) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // keys inside one warp are mostly distinct (levels x classes), so plain shared-memory atomics
-            // beat warp aggregation (match.any costs one round per distinct key)
-            if (k[j] & KEY_READY) atomicAdd(&s_hist[key_level(k[j]) * Q + key_class(k[j])], 1u);
-        }
-    }
-    __syncthreads();
-    u32* row = table + (size_t)blockIdx.x * G;
-    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
-        const u32 v = s_hist[g];
-        row[g] = v;
-        if (v) atomicAdd(&total[g], v);
-    }
-}
-

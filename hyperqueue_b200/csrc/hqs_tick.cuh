@@ -1,0 +1,1209 @@
+// hqs_tick.cuh — tick_k: ONE cooperative kernel per scheduler tick.  Included by hqsched.cu inside its
+// anonymous namespace (after hqs_ready_set.cuh and hqs_solver.cuh).
+//
+//   CTA 0 ("solver CTA")     stages the worker state, the class table and the tick's orders in shared memory
+//                            (straight from the pinned host buffer, while the other CTAs count), waits for the
+//                            histogram, compacts the non-empty (priority level, class) groups and then ONE warp
+//                            walks them in priority order: a sparse first-fit over tiles of 32 workers (lane =
+//                            worker) that starts at the class's frontier tile — the first tile that may still
+//                            hold a worker with room for the class — so a group costs one or two tile visits
+//                            instead of a block-wide scan.  The other 15 warps sleep on a named barrier and are
+//                            woken for the block-parallel steps (quotas / capping of the packed level, restarts
+//                            of the min-utilisation rule).
+//   CTAs 1.. ("worker CTAs") count: per-chunk histogram of the ready tasks by group (4 B/slot streamed from HBM);
+//                            scan:  exclusive prefix of the chunk table over chunks, one warp per group column;
+//                            pack:  on request, one warp fills one worker (pack_body, the first saturated level);
+//                            emit:  stable rank of every ready task inside its group -> count segment ->
+//                                   (worker, variant), 8-byte assignment, READY -> DONE.
+// Phases are ordered by acquire/release counters in global memory (TickSync); every wait has a time-out, so a
+// broken grid fails the tick instead of hanging the GPU.  A sharded tick (several GPUs) exchanges the per-group
+// counts by NVLink peer stores from the solver CTA between the histogram and the solve.
+#pragma once
+
+constexpr u32 TICK_THREADS = 512;
+constexpr u32 TICK_WARPS = TICK_THREADS / 32;
+constexpr u32 EMIT_ROWS_MAX = 16;     // rows of 32 tasks per emit warp and chunk
+constexpr u32 EMIT_SEG_SMEM = 1024;   // count segments cached in shared memory by the emit step
+constexpr u32 CMD_PACK = 1, CMD_EMIT = 2, CMD_EXIT = 3;      // grid commands: cmd word = (sequence << 2) | type
+constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3;    // block commands inside the solver CTA
+constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4;
+constexpr u32 SM_NONE = 0xFFFFFFFFu;
+constexpr u32 MU_MAX_PASSES = 8;      // restarts of the min-utilisation rule before the remaining violators are dropped
+
+struct TickSync {
+    u32 cmd;          // grid command of the solver CTA
+    u32 count_done;   // worker CTAs that finished their histograms
+    u32 scan_done;    // worker CTAs that finished their part of the column scan
+    u32 pack_done;    // worker CTAs that finished the current pack command (cumulative)
+    u32 emit_done;    // worker CTAs that left the kernel's work loop
+    u32 error;        // 2 = a wait timed out
+    u32 pad[2];
+};
+
+// offsets into the solver CTA's dynamic shared memory (SM_NONE: the array stays in global memory)
+struct TickSmem {
+    u32 fr, rem, unt, remtime, excl, td, frontier, glist, gcl;     // always staged
+    u32 classes, vorder, blocked, bef, loc;                        // optional
+};
+
+struct TickArgs {
+    // tick input: device-visible copy of the host staging buffer (pinned host memory read in place, or its device copy)
+    const u64* free_rw;      // [W][R]
+    const u64* total_rw;     // [W][R]
+    const u64* rem_time;     // [W]
+    const u32* order;        // [Q] class ids in processing order inside one priority level
+    const uint8_t* vorder;   // [Q][HQS_MAX_VARIANTS] variant ids, first = the tick's demand variant
+    const uint8_t* blocked;  // [W][Q] bytes (bit v) or nullptr
+    const float* min_util;   // [W] or nullptr (no worker has a minimum utilisation)
+    const void* classes;     // ClassT<RT, AT>[Q] of the solver's width
+    const void* classes64;   // ClassT<RT, u64>[Q] (the pack warps work on exact amounts)
+    u64 gscale[HQS_MAX_RESOURCES];   // narrow path: amount = scaled amount * gscale[r] (+ a per-worker remainder)
+    u32 W, Q, L, R, G;
+    u32 classes_bytes;       // Q * sizeof(ClassT<RT, AT>)
+    u32 flags;               // TF_*
+    u32 any_time_limit;      // some worker has a finite remaining time
+    // task table / chunk geometry
+    u32* key;
+    u32 n_handles, chunk, rows, P, nbits, emit_warps, g_smem;
+    // counts
+    u32* total_local;        // [G] ready tasks of this rank per group (count step; zeroed at the end of the tick)
+    const u32* total_ext;    // [G] counts summed over ranks, provided by the host (NCCL variant) or nullptr
+    const u32* before_ext;   // [G] counts of lower ranks (NCCL variant) or nullptr
+    u32* table;              // [P][G]
+    // outputs
+    GroupOut* gout;          // [G]
+    u32* seg_cum;            // [SEG_CAP] inclusive end rank of the segment inside its group
+    u32* seg_wv;             // [SEG_CAP] worker | variant << 16
+    u64* free_after;         // [W][R] device copy
+    TickHeaderOut* hdr;      // device copy
+    TickHeaderOut* hdr_host; // pinned host mirror: header followed by free_after [W][R] (read by hqs_tick_fetch)
+    hqs_assignment* out;
+    u32 out_cap;
+    u32* rem_scratch;        // [W][RT] u64 as u32 pairs: narrow remainders when they do not fit shared memory
+    // peer-to-peer count exchange (sharded tick without a host collective): x_world == 0 => off
+    u32* x_peer[HQS_MAX_PEERS];   // base of every rank's exchange buffer (own included)
+    u32* x_all;              // [G] out: sum over ranks
+    u32* x_before;           // [G] out: sum over lower ranks
+    u32 x_world, x_rank, x_seq;
+    // synchronisation, pack
+    TickSync* sync;
+    PackScratch pk;
+    uint8_t* excl_glob;      // [W] workers excluded by the min-utilisation rule (read by the pack warps)
+    TickSmem sm;
+    u32 smem_solver;         // bytes of the solver layout (debug)
+};
+
+__device__ __forceinline__ void bar_named(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// thread 0 of a CTA: wait until *p >= target (counters restart at zero every tick)
+__device__ __forceinline__ bool spin_until_ge(const u32* p, u32 target) {
+    const long long t0 = clock64();
+    while (ld_acquire(p) < target) {
+        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) return false;
+        __nanosleep(40);
+    }
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// lanes of the warp holding the same group id, in constant time: one ballot per key bit (match.any
+// iterates once per DISTINCT key, and a warp of 32 tasks holds ~30 distinct (level, class) keys)
+__device__ __forceinline__ u32 same_key_lanes(u32 act, u32 g, u32 nbits) {
+    u32 peers = act;
+    for (u32 b = 0; b < nbits; ++b) {
+        const u32 bit = (g >> b) & 1u;
+        const u32 bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
+// =================================================================================================
+// worker CTAs
+// =================================================================================================
+// count: histogram of the ready tasks of chunk b by group -> table row b, totals.  4 B read per table slot.
+__device__ void count_chunk(const TickArgs& a, u32 b, u32* s_hist) {
+    const u32 G = a.G, Q = a.Q;
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) s_hist[g] = 0;
+    __syncthreads();
+    const u32 base = b * a.chunk;
+    const u32 end = min(base + a.chunk, a.n_handles);
+    // chunk and base are multiples of 512 => 16-byte aligned uint4 loads; a ragged tail is scalar
+    const u32 vec_end = base + ((end - base) & ~3u);
+    for (u32 rowb = base; rowb < end; rowb += blockDim.x * 8) {
+        // two independent 16-byte loads in flight per thread
+        u32 k[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u32 i = rowb + h * blockDim.x * 4 + threadIdx.x * 4;
+            if (i + 4 <= vec_end) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.key + i));
+                k[4 * h] = v.x; k[4 * h + 1] = v.y; k[4 * h + 2] = v.z; k[4 * h + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) k[4 * h + j] = (i + j < end) ? __ldg(a.key + i + j) : 0u;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // keys inside one warp are mostly distinct (levels x classes), so plain shared-memory atomics
+            // beat warp aggregation (match.any costs one round per distinct key)
+            if (k[j] & KEY_READY) atomicAdd(&s_hist[key_level(k[j]) * Q + key_class(k[j])], 1u);
+        }
+    }
+    __syncthreads();
+    u32* row = a.table + (size_t)b * G;
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+        const u32 v = s_hist[g];
+        row[g] = v;
+        if (v) atomicAdd(&a.total_local[g], v);
+    }
+    __syncthreads();
+}
+
+// emit: stable (handle-ordered) rank of every ready task of chunk b inside its group, rank -> placement.
+// Each warp owns a.rows rows of 32 consecutive tasks; per-warp group counters live in shared memory:
+//   s_cnt[w][g]  first pass: tasks of group g in warp w's rows; then the rank at which warp w's first task of
+//                group g starts; second pass: running counter.
+// HBM traffic: 4 B read per table slot (L2 hit: the count step read it microseconds ago), 8 B written per
+// assignment, 4 B key write-back per assignment.
+__device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut* s_go, const u32* s_segc, const u32* s_segw,
+                           bool seg_smem, const u32* before) {
+    const u32 G = a.G, Q = a.Q, nwarps = a.emit_warps, rows = a.rows;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // A chunk holds an assigned task only if, for some group, fewer than k[g] tasks of the group precede
+    // the chunk (the assigned ones are the first k[g] in handle order): in a drain tick only the first
+    // chunks qualify, the rest leave after reading one table row.
+    const u32* row = a.table + (size_t)b * G;
+    {
+        bool mine = false;
+        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+            const u32 bef = before ? __ldcg(before + g) : 0u;
+            const u32 k = a.g_smem ? s_go[g].k : __ldcg(&a.gout[g].k);
+            mine |= __ldcg(row + g) + bef < k;
+        }
+        if (!__syncthreads_or(mine)) return;
+    }
+    for (u32 i = threadIdx.x; i < nwarps * G; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const u32 base = b * a.chunk;
+    const u32 end = min(base + a.chunk, a.n_handles);
+    const bool active = warp < nwarps;
+    const u32 wbeg = base + warp * (32 * rows);
+    u32* mycnt = s_cnt + (active ? warp : 0) * G;
+    u32 kk[EMIT_ROWS_MAX], peers[EMIT_ROWS_MAX];
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
+        const u32 i = wbeg + j * 32 + lane;
+        kk[j] = (active && j < (int)rows && i < end) ? a.key[i] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
+        peers[j] = 0;
+        if (active && j < (int)rows) {                       // warp-uniform
+            const bool ready = (kk[j] & KEY_READY) != 0;
+            const u32 g = key_level(kk[j]) * Q + key_class(kk[j]);
+            const u32 act = __ballot_sync(0xffffffffu, ready);
+            u32 pm = same_key_lanes(act, g, a.nbits);
+            if (!ready) pm = 0;
+            peers[j] = pm;
+            // pass 1: per-warp counts (rows in order; the leader of each key adds its lanes)
+            if (ready && (u32)(__ffs(pm) - 1) == lane) mycnt[g] += __popc(pm);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // turn counts into starting ranks: rank0(w, g) = table[b][g] + sum_{w' < w} cnt[w'][g]
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+        u32 run = __ldcg(row + g);
+        for (u32 w2 = 0; w2 < nwarps; ++w2) {
+            const u32 c = s_cnt[w2 * G + g];
+            s_cnt[w2 * G + g] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // pass 2: rank and emit
+#pragma unroll
+    for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
+        if (active && j < (int)rows) {                       // warp-uniform
+            const u32 i = wbeg + j * 32 + lane;
+            const u32 k = kk[j], pm = peers[j];
+            const u32 g = key_level(k) * Q + key_class(k);
+            if (pm) {
+                const u32 leader = __ffs(pm) - 1;
+                u32 r0 = 0;
+                if (leader == lane) {
+                    r0 = mycnt[g];
+                    mycnt[g] = r0 + __popc(pm);
+                }
+                r0 = __shfl_sync(pm, r0, leader);
+                const u32 r_loc = r0 + __popc(pm & ((1u << lane) - 1));      // rank among this rank's tasks
+                const u32 bef = before ? __ldcg(before + g) : 0u;
+                GroupOut go;
+                if (a.g_smem) go = s_go[g];
+                else {
+                    const uint4 gv = __ldcg(reinterpret_cast<const uint4*>(a.gout + g));
+                    go.k = gv.x; go.out_off = gv.y; go.seg_lo = gv.z; go.seg_n = gv.w;
+                }
+                if (r_loc + bef < go.k) {
+                    const u32 r = r_loc + bef;                                // global rank in the group
+                    // first segment whose inclusive end rank exceeds r
+                    u32 lo = go.seg_lo, hi = go.seg_lo + go.seg_n;
+                    u32 wv;
+                    if (seg_smem) {
+                        while (lo < hi) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (s_segc[mid] > r) hi = mid; else lo = mid + 1;
+                        }
+                        wv = s_segw[lo];
+                    } else {
+                        while (lo < hi) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (__ldcg(a.seg_cum + mid) > r) hi = mid; else lo = mid + 1;
+                        }
+                        wv = __ldcg(a.seg_wv + lo);
+                    }
+                    const u32 oi = go.out_off + r_loc;
+                    if (oi < a.out_cap) {
+                        hqs_assignment asg;
+                        asg.task = i;
+                        asg.worker = (uint16_t)(wv & 0xFFFFu);
+                        asg.variant = (uint8_t)((wv >> 16) & 0xFFu);
+                        asg.kind = 0;
+                        a.out[oi] = asg;
+                        a.key[i] = (k & ~KEY_READY) | KEY_DONE;               // Waiting -> Assigned
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+template <int RT>
+__device__ void worker_cta(const TickArgs& a, unsigned char* smem) {
+    __shared__ u32 s_cmd, s_ok;
+    u32* s_u32 = reinterpret_cast<u32*>(smem);
+    const u32 nW = gridDim.x - 1, me = blockIdx.x - 1;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool ok = true;
+    // ---- count
+    if (a.flags & TF_COUNT) {
+        for (u32 b = me; b < a.P; b += nW) count_chunk(a, b, s_u32);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&a.sync->count_done, 1u);
+            s_ok = spin_until_ge(&a.sync->count_done, nW) ? 1u : 0u;
+        }
+        __syncthreads();
+        ok = s_ok != 0;
+    }
+    // ---- scan: exclusive prefix over chunks, one warp per group column, 32 chunk rows per step
+    if (ok) {
+        for (u32 g = me * TICK_WARPS + warp; g < a.G; g += nW * TICK_WARPS) {
+            u32 carry = 0;
+            for (u32 b0 = 0; b0 < a.P; b0 += 32) {
+                const u32 b = b0 + lane;
+                const u32 v = b < a.P ? __ldcg(a.table + (size_t)b * a.G + g) : 0;
+                u32 inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                    if ((int)lane >= d) inc += y;
+                }
+                if (b < a.P) a.table[(size_t)b * a.G + g] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&a.sync->scan_done, 1u);
+    }
+    // ---- command loop
+    u32 seen = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            u32 cmd = 0;
+            if (ok) {
+                const long long t0 = clock64();
+                while ((cmd = ld_acquire(&a.sync->cmd)) == seen) {
+                    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { cmd = 0; break; }
+                    __nanosleep(100);
+                }
+            }
+            if (cmd == 0 || cmd == seen) { atomicExch(&a.sync->error, 2u); cmd = CMD_EXIT; }
+            s_cmd = cmd;
+        }
+        __syncthreads();
+        const u32 cmd = s_cmd;
+        __syncthreads();
+        seen = cmd;
+        const u32 type = cmd & 3u;
+        if (type == CMD_PACK) {
+            PackArgs p;
+            p.pk = a.pk; p.total_rw = a.total_rw; p.rem_time = a.rem_time; p.blocked = a.blocked;
+            p.excluded = a.min_util ? a.excl_glob : nullptr; p.classes64 = a.classes64; p.W = a.W; p.Q = a.Q; p.R = a.R;
+            pack_body<RT>(p, smem);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&a.sync->pack_done, 1u);
+            continue;
+        }
+        if (type == CMD_EMIT) {
+            if (threadIdx.x == 0) s_ok = spin_until_ge(&a.sync->scan_done, nW) ? 1u : 0u;
+            __syncthreads();
+            if (s_ok) {
+                const u32 G = a.G;
+                u32* s_cnt = s_u32;                                                      // [emit_warps][G]
+                GroupOut* s_go = reinterpret_cast<GroupOut*>(s_u32 + a.emit_warps * G);    // [G] when g_smem
+                u32* s_segc = reinterpret_cast<u32*>(s_go + (a.g_smem ? G : 0));          // [EMIT_SEG_SMEM]
+                u32* s_segw = s_segc + EMIT_SEG_SMEM;
+                const u32 n_seg = __ldcg(&a.hdr->n_segments);
+                const bool seg_smem = n_seg <= EMIT_SEG_SMEM;
+                const u32* before = a.x_world ? a.x_before : a.before_ext;
+                if (me < a.P) {
+                    if (a.g_smem)
+                        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+                            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(a.gout + g));
+                            GroupOut go; go.k = v.x; go.out_off = v.y; go.seg_lo = v.z; go.seg_n = v.w;
+                            s_go[g] = go;
+                        }
+                    if (seg_smem)
+                        for (u32 i = threadIdx.x; i < n_seg; i += blockDim.x) { s_segc[i] = __ldcg(a.seg_cum + i); s_segw[i] = __ldcg(a.seg_wv + i); }
+                    __syncthreads();
+                    for (u32 b = me; b < a.P; b += nW) emit_chunk(a, b, s_cnt, s_go, s_segc, s_segw, seg_smem, before);
+                }
+            } else if (threadIdx.x == 0) {
+                atomicExch(&a.sync->error, 2u);
+            }
+        }
+        break;      // CMD_EMIT or CMD_EXIT
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&a.sync->emit_done, 1u);
+    }
+}
+
+// =================================================================================================
+// solver CTA
+// =================================================================================================
+template <int RT, typename AT>
+__device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
+    constexpr bool NARROW = sizeof(AT) == 4;
+    constexpr AT AMAX = AmountMax<AT>::value;
+    using Var = VarT<RT, AT>;
+    using Cls = ClassT<RT, AT>;
+    __shared__ u64 s_C[HQS_MAX_RESOURCES], s_totmax[HQS_MAX_RESOURCES], s_D[HQS_MAX_RESOURCES];
+    __shared__ u64 s_red[TICK_WARPS * (HQS_MAX_RESOURCES + 1)];
+    __shared__ u64 s_qT[PACK_MAX_CAND];
+    __shared__ u32 s_wcnt[TICK_WARPS];
+    __shared__ u32 s_pkpos[PACK_MAX_CAND], s_pknseg[PACK_MAX_CAND], s_pkseglo[PACK_MAX_CAND], s_pkex[PACK_MAX_CAND], s_cbase[PACK_MAX_CAND + 1];
+    __shared__ u32 s_blk[8];            // block command: type, li, lj, seg region base, phi (2 words), n_packs
+    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 W = a.W, Q = a.Q, R = a.R, G = a.G;
+    const u32 nW = gridDim.x - 1;
+    const u32 n_tiles = (W + 31) / 32;
+    const long long t_start = clock64();
+    const unsigned long long gt_start = global_timer_ns();
+
+    // ---- shared-memory layout
+    AT* s_fr = reinterpret_cast<AT*>(smem + a.sm.fr);                                  // [W][RT]
+    u32* s_unt = reinterpret_cast<u32*>(smem + a.sm.unt);                              // [W] bit r: free == total != 0
+    u64* s_remtime = reinterpret_cast<u64*>(smem + a.sm.remtime);                      // [W]
+    uint8_t* s_excl = smem + a.sm.excl;                                                // [W]
+    unsigned short* s_td = reinterpret_cast<unsigned short*>(smem + a.sm.td);          // [W] tried | dead << 8 of the current group
+    unsigned short* s_front = reinterpret_cast<unsigned short*>(smem + a.sm.frontier); // [Q] first tile that may have room
+    uint2* s_glist = reinterpret_cast<uint2*>(smem + a.sm.glist);                      // [L*Q] (group, count)
+    u32* s_gcl = reinterpret_cast<u32*>(smem + a.sm.gcl);                              // [L*Q] class | level << 16
+    // narrow remainders (exact amount = fr * gscale + rem): shared memory when they fit, else global scratch
+    u64* p_rem = NARROW ? (a.sm.rem != SM_NONE ? reinterpret_cast<u64*>(smem + a.sm.rem) : reinterpret_cast<u64*>(a.rem_scratch)) : nullptr;
+    const Cls* classes = a.sm.classes != SM_NONE ? reinterpret_cast<const Cls*>(smem + a.sm.classes) : reinterpret_cast<const Cls*>(a.classes);
+    const uint8_t* vorder = a.sm.vorder != SM_NONE ? smem + a.sm.vorder : a.vorder;
+    const uint8_t* blocked = a.blocked ? (a.sm.blocked != SM_NONE ? smem + a.sm.blocked : a.blocked) : nullptr;
+    u32* s_bef = a.sm.bef != SM_NONE ? reinterpret_cast<u32*>(smem + a.sm.bef) : nullptr;
+    u32* s_loc = a.sm.loc != SM_NONE ? reinterpret_cast<u32*>(smem + a.sm.loc) : nullptr;
+
+    auto exact_of = [&](AT f, u32 w, int r) -> u64 {
+        if constexpr (NARROW) return f == AMAX ? HQS_AMOUNT_MAX : (u64)f * a.gscale[r] + p_rem[(size_t)w * RT + r];
+        else return f;
+    };
+    auto exact_amount = [&](const Var& dv, int r) -> u64 {
+        if constexpr (NARROW) return (u64)dv.amount[r] * a.gscale[r];
+        else return dv.amount[r];
+    };
+    // (re)stage the worker state from the tick input; thread per worker
+    auto stage_workers = [&]() {
+        for (u32 w = tid; w < W; w += blockDim.x) {
+            u32 unt = 0;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const u64 n = r < (int)R ? a.free_rw[(size_t)w * R + r] : 0;
+                const u64 t = r < (int)R ? a.total_rw[(size_t)w * R + r] : 0;
+                if constexpr (NARROW) {
+                    const u64 g = a.gscale[r];
+                    const u64 nq = g == 1 ? n : n / g;
+                    s_fr[(size_t)w * RT + r] = n == HQS_AMOUNT_MAX ? AMAX : (AT)nq;
+                    p_rem[(size_t)w * RT + r] = n == HQS_AMOUNT_MAX ? 0 : n - nq * g;
+                } else {
+                    s_fr[(size_t)w * RT + r] = n;
+                }
+                unt |= (t != 0 && n == t) ? (1u << r) : 0u;
+            }
+            s_unt[w] = unt;
+        }
+    };
+    // s_C[r] = sum over workers of the exact free amount, saturating (MAX absorbs); warp r handles resource r (+16 ...)
+    auto sum_free_block = [&]() {
+        for (u32 r = warp; r < R; r += TICK_WARPS) {
+            u64 v = 0;
+            for (u32 w = lane; w < W; w += 32) v = sat_add64(v, s_excl[w] ? 0 : exact_of(s_fr[(size_t)w * RT + r], w, (int)r));
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v = sat_add64(v, __shfl_xor_sync(0xffffffffu, v, d));
+            if (lane == 0) s_C[r] = v;
+        }
+    };
+
+    // ---- prologue A: staging (overlaps the histogram of the worker CTAs)
+    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; }
+    if (tid < HQS_MAX_RESOURCES) { s_totmax[tid] = 0; s_D[tid] = 0; s_C[tid] = 0; }
+    if (a.sm.classes != SM_NONE) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.classes);
+        uint4* dst = reinterpret_cast<uint4*>(smem + a.sm.classes);
+        for (u32 i = tid; i < a.classes_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    if (a.sm.vorder != SM_NONE)
+        for (u32 i = tid; i < Q * HQS_MAX_VARIANTS; i += blockDim.x) smem[a.sm.vorder + i] = a.vorder[i];
+    if (a.blocked && a.sm.blocked != SM_NONE) {
+        const u32 nb = W * Q;
+        if ((nb & 15u) == 0 && ((size_t)a.blocked & 15u) == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.blocked);
+            uint4* dst = reinterpret_cast<uint4*>(smem + a.sm.blocked);
+            for (u32 i = tid; i < nb / 16; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for (u32 i = tid; i < nb; i += blockDim.x) smem[a.sm.blocked + i] = a.blocked[i];
+        }
+    }
+    for (u32 w = tid; w < W; w += blockDim.x) {
+        s_remtime[w] = a.rem_time[w];
+        s_excl[w] = 0;
+        if (a.min_util) a.excl_glob[w] = 0;
+    }
+    for (u32 c = tid; c < Q; c += blockDim.x) s_front[c] = 0;
+    __syncthreads();
+    stage_workers();
+    // per-resource maximum of the (scaled) worker totals: a class no worker is big enough for is not demand
+    for (u32 w = tid; w < W; w += blockDim.x) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (r >= (int)R) continue;
+            const u64 t = a.total_rw[(size_t)w * R + r];
+            u64 tq = t;
+            if constexpr (NARROW) tq = t == HQS_AMOUNT_MAX ? (u64)AMAX : (a.gscale[r] == 1 ? t : t / a.gscale[r]);
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_totmax[r]), (unsigned long long)tq);
+        }
+    }
+    // groups without ready tasks keep k = 0 (the emit step's chunk filter reads k of every group)
+    for (u32 g = tid; g < G; g += blockDim.x) a.gout[g].k = 0;
+    __syncthreads();
+    sum_free_block();
+
+    // ---- prologue B: wait for the histogram; sharded: exchange the count vectors over NVLink
+    if (a.flags & TF_COUNT) {
+        if (tid == 0 && !spin_until_ge(&a.sync->count_done, nW)) s_err = 2;
+    }
+    __syncthreads();
+    const long long t_counted = clock64();
+    const u32* tot_all = a.total_ext ? a.total_ext : a.total_local;
+    const u32* before = a.before_ext;
+    if (a.x_world) {
+        // block-strided peer stores of my count vector into every rank's exchange buffer (own included), a system
+        // fence, then one release flag per peer; afterwards acquire every rank's flag of THIS tick
+        const u32 parity = a.x_seq & 1u;
+        for (u32 r = 0; r < a.x_world; ++r) {
+            u32* dst = a.x_peer[r] + ((size_t)parity * HQS_MAX_PEERS + a.x_rank) * HQS_MAX_GROUPS;
+            for (u32 g = tid; g < G; g += blockDim.x) dst[g] = __ldcg(a.total_local + g);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.x_world) {
+            u32* flags = a.x_peer[tid] + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
+            st_release_sys(flags + a.x_rank, a.x_seq);
+        }
+        if (tid < a.x_world) {
+            const u32* myflags = a.x_peer[a.x_rank] + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(myflags + tid) != a.x_seq) {
+                if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { s_err = 2; break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        const u32* xc = a.x_peer[a.x_rank] + (size_t)parity * HQS_MAX_PEERS * HQS_MAX_GROUPS;
+        for (u32 g = tid; g < G; g += blockDim.x) {
+            u32 all = 0, bef = 0;
+            for (u32 r = 0; r < a.x_world; ++r) {
+                const u32 v = __ldcg(xc + (size_t)r * HQS_MAX_GROUPS + g);     // peers wrote it: bypass L1
+                all += v;
+                bef += r < a.x_rank ? v : 0u;
+            }
+            a.x_all[g] = all;
+            a.x_before[g] = bef;
+        }
+        __syncthreads();
+        tot_all = a.x_all;
+        before = a.x_before;
+    }
+
+    // ---- prologue C: compact the non-empty groups in processing order: level asc (= priority desc), then the
+    //      tick's class order.  Every warp owns a contiguous range of positions; two passes, one barrier.
+    {
+        const u32 n_pos = a.L * Q;
+        const u32 seg = ((n_pos + TICK_WARPS - 1) / TICK_WARPS + 31) & ~31u;      // positions per warp, multiple of 32
+        u32 nn[HQS_MAX_GROUPS / TICK_WARPS / 32], gg[HQS_MAX_GROUPS / TICK_WARPS / 32];
+        u32 cnt = 0;
+#pragma unroll
+        for (int i = 0; i < (int)(HQS_MAX_GROUPS / TICK_WARPS / 32); ++i) {
+            nn[i] = 0; gg[i] = 0;
+            const u32 pos = warp * seg + i * 32 + lane;
+            if ((u32)i * 32 < seg && pos < n_pos) {
+                const u32 lvl = pos / Q, j = pos - lvl * Q;
+                gg[i] = lvl * Q + a.order[j];
+                nn[i] = __ldcg(tot_all + gg[i]);
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, nn[i] != 0));
+        }
+        if (lane == 0) s_wcnt[warp] = cnt;
+        __syncthreads();
+        u32 off = 0, tot = 0;
+        for (u32 w2 = 0; w2 < TICK_WARPS; ++w2) { const u32 c2 = s_wcnt[w2]; off += w2 < warp ? c2 : 0; tot += c2; }
+#pragma unroll
+        for (int i = 0; i < (int)(HQS_MAX_GROUPS / TICK_WARPS / 32); ++i) {
+            const u32 bal = __ballot_sync(0xffffffffu, nn[i] != 0);
+            if (nn[i]) {
+                const u32 slot = off + __popc(bal & ((1u << lane) - 1));
+                const u32 g = gg[i];
+                s_glist[slot] = make_uint2(g, nn[i]);
+                s_gcl[slot] = (g % Q) | ((g / Q) << 16);
+                if (before) {
+                    if (s_bef) { s_bef[slot] = __ldcg(before + g); s_loc[slot] = __ldcg(a.total_local + g); }
+                }
+            }
+            off += __popc(bal);
+        }
+        if (tid == 0) s_nlist = tot;
+        __syncthreads();
+    }
+    const u32 n_list = s_nlist;
+    // ---- prologue D: can ANY level be saturated?  If every class has one variant and no `All` entry, a level's
+    //      demand never exceeds (total demand - what earlier levels consumed), so "total demand fits the pool"
+    //      rules saturation out for the whole tick and the per-level tests are skipped (mode M1).
+    bool skip_sat = (a.flags & TF_PACK) == 0;
+    if (!skip_sat) {
+        u64 val[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) val[r] = 0;
+        u32 multi = 0;
+        for (u32 e = tid; e < n_list; e += blockDim.x) {
+            const u32 c = s_gcl[e] & 0xFFFFu, n = s_glist[e].y;
+            const Cls& cl = classes[c];
+            if (cl.n_variants > 1) multi = 1;
+            const Var& dv = cl.v[vorder[c * HQS_MAX_VARIANTS]];
+            if (dv.all_mask) multi = 1;
+            bool servable = true;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) servable &= (u64)dv.amount[r] <= s_totmax[r];
+            if (servable) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r) val[r] = sat_add64(val[r], sat_mul64(exact_amount(dv, r), (u64)n));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) val[r] = sat_add64(val[r], __shfl_xor_sync(0xffffffffu, val[r], d));
+        }
+        if (__any_sync(0xffffffffu, multi) && lane == 0) s_multi = 1;
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) s_red[warp * RT + r] = val[r];
+        }
+        __syncthreads();
+        if (tid < RT) {
+            u64 d = 0;
+            for (u32 w2 = 0; w2 < TICK_WARPS; ++w2) d = sat_add64(d, s_red[w2 * RT + tid]);
+            s_D[tid] = d;
+        }
+        __syncthreads();
+        bool fits = s_multi == 0;
+        for (u32 r = 0; r < R; ++r) fits &= s_C[r] == HQS_AMOUNT_MAX || s_D[r] <= s_C[r];
+        skip_sat = fits;
+    }
+    __syncthreads();
+    const long long t_prologue = clock64();
+
+    // =============================================================================================
+    // block-parallel steps, executed by ALL warps of the CTA (the solver warp calls block_work after waking the others)
+    // =============================================================================================
+    auto block_work = [&](u32 cmd) {
+        if (cmd == BLK_RESTART) {
+            // min-utilisation restart: excluded workers stay out, everything else starts over
+            stage_workers();
+            for (u32 c = tid; c < Q; c += blockDim.x) s_front[c] = 0;
+            bar_named(2, TICK_THREADS);
+            return;
+        }
+        // ---- BLK_PACK: the level [li, lj) is saturated
+        const u32 li = s_blk[1], lj = s_blk[2], region0 = s_blk[3];
+        const u32 ng = lj - li;
+        const double phi = __hiloint2double((int)s_blk[5], (int)s_blk[4]);
+        if (tid < PACK_MAX_CAND) s_qT[tid] = 0;
+        if (tid == 0) {
+            u32 ci = 0;
+            for (u32 e = li; e < lj; ++e) {
+                const u32 c = s_gcl[e] & 0xFFFFu;
+                s_cbase[e - li] = ci;
+                for (u32 v = 0; v < classes[c].n_variants; ++v) a.pk.cand[ci++] = c | (v << 16) | ((e - li) << 24);
+            }
+            s_cbase[ng] = ci;
+            a.pk.meta[0] = ci;
+            a.pk.meta[1] = ng;
+        }
+        bar_named(2, TICK_THREADS);
+        // a. quotas: share of each class proportional to how many fit on the worker alone.  Pass 1: every worker's
+        //    own count per group (stashed in its quota slot) and the pool sums; pass 2: the quotas.
+        for (u32 w0 = 0; w0 < W; w0 += blockDim.x) {
+            const u32 w = w0 + tid;
+            const bool has = w < W && !s_excl[w];
+            AT fr[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) fr[r] = has ? s_fr[(size_t)w * RT + r] : 0;
+            const u32 unt = has ? s_unt[w] : 0;
+            const u64 rt = has ? s_remtime[w] : 0;
+            for (u32 e = li; e < lj; ++e) {
+                const u32 c = s_gcl[e] & 0xFFFFu, n = s_glist[e].y;
+                u64 cn = 0;
+                if (has) {
+                    const uint8_t blk = blocked ? blocked[(size_t)w * Q + c] : 0;
+                    for (u32 v = 0; v < classes[c].n_variants; ++v) {
+                        const Var& dv = classes[c].v[v];
+                        if (!admissible(dv, v, blk, rt)) continue;
+                        const u64 f = fit_count<RT>(fr, unt, dv, n);
+                        cn = f > cn ? f : cn;
+                    }
+                }
+                if (w < W) a.pk.quota[(size_t)w * PACK_MAX_CAND + (e - li)] = (u32)cn;       // cn <= n < 2^32
+                u64 x = cn;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                if (lane == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(&s_qT[e - li]), (unsigned long long)x);
+            }
+        }
+        bar_named(2, TICK_THREADS);
+        for (u32 w = tid; w < W; w += blockDim.x) {
+            for (u32 e = li; e < lj; ++e) {
+                const u32 n = s_glist[e].y;
+                const u64 T = s_qT[e - li];
+                const u64 cn = a.pk.quota[(size_t)w * PACK_MAX_CAND + (e - li)];           // this thread's own store
+                const u64 q = T ? ((u64)n * cn + T - 1) / T : 0;
+                const u64 q_phi = __double2ull_ru(__dmul_rn(__ull2double_rn(q), phi));     // ceil(q * phi)
+                a.pk.quota[(size_t)w * PACK_MAX_CAND + (e - li)] = (u32)q_phi;
+            }
+            // b. publish the worker state for the pack warps
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                if (r < (int)R) a.pk.fr[(size_t)w * R + r] = exact_of(s_fr[(size_t)w * RT + r], w, r);
+            if (a.min_util) a.excl_glob[w] = s_excl[w];
+        }
+        __threadfence();
+        bar_named(2, TICK_THREADS);
+        if (tid == 0) {
+            const u32 np = s_npacks + 1;
+            s_npacks = np;
+            st_release(&a.sync->cmd, (np << 2) | CMD_PACK);
+            if (!spin_until_ge(&a.sync->pack_done, np * nW)) s_err = 2;
+        }
+        bar_named(2, TICK_THREADS);
+        // c. the workers filled themselves: take their free vectors back
+        for (u32 w = tid; w < W; w += blockDim.x) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                if (r < (int)R) {
+                    const u64 x = __ldcg(a.pk.fr + (size_t)w * R + r);
+                    if constexpr (NARROW) {
+                        const u64 g = a.gscale[r], rm = p_rem[(size_t)w * RT + r];
+                        s_fr[(size_t)w * RT + r] = x == HQS_AMOUNT_MAX ? AMAX : (AT)(g == 1 ? x - rm : (x - rm) / g);
+                    } else {
+                        s_fr[(size_t)w * RT + r] = x;
+                    }
+                }
+        }
+        bar_named(2, TICK_THREADS);
+        // d. cap what the workers took for each class at its count, (variant, worker) order: one warp per group of the
+        //    level, count segments into the group's own region.  The excess (what a worker took beyond the class count)
+        //    replaces the worker's `taken` entry; the solver warp hands it back when it reaches the group — the
+        //    specification interleaves hand-backs and first-fit group by group.
+        for (u32 gi = warp; gi < ng; gi += TICK_WARPS) {
+            const u32 e = li + gi;
+            const u32 c = s_gcl[e] & 0xFFFFu, n = s_glist[e].y;
+            const u32 nv = classes[c].n_variants;
+            const u32 seglo = region0 + 2u * W * s_cbase[gi];
+            u32 pos = 0, nseg = 0, ex_lo = 0xFFFFu, ex_hi = 0;
+            for (u32 v = 0; v < nv; ++v) {
+                const Var& dv = classes[c].v[v];
+                for (u32 tile = 0; tile < n_tiles; ++tile) {
+                    const u32 w = tile * 32 + lane;
+                    u32* tk = a.pk.taken + (size_t)w * PACK_MAX_CAND + s_cbase[gi] + v;
+                    const u32 k = w < W ? __ldcg(tk) : 0;
+                    if (__ballot_sync(0xffffffffu, k != 0) == 0) continue;
+                    u64 inc = k;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+                        if ((int)lane >= d) inc += y;
+                    }
+                    const u64 room = n - pos, exc = inc - k;
+                    u32 use = 0;
+                    if (k && exc < room) use = (u32)((u64)k < room - exc ? (u64)k : room - exc);
+                    const u32 um = __ballot_sync(0xffffffffu, use != 0);
+                    if (use) {
+                        const u32 si = seglo + nseg + __popc(um & ((1u << lane) - 1));
+                        if (si < SEG_CAP) { a.seg_cum[si] = pos + (u32)exc + use; a.seg_wv[si] = w | (v << 16); }
+                        // what stays on the worker makes its resources "touched" (free != total); an unbounded amount stays
+                        u32 touched = 0;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            if (((dv.used_mask >> r) & 1) && s_fr[(size_t)w * RT + r] != AMAX) touched |= 1u << r;
+                        atomicAnd(&s_unt[w], ~touched);
+                    }
+                    if (k) *tk = k - use;
+                    if (__ballot_sync(0xffffffffu, k > use)) { ex_lo = ex_lo < tile ? ex_lo : tile; ex_hi = tile + 1; }
+                    nseg += __popc(um);
+                    const u64 total = __shfl_sync(0xffffffffu, inc, 31);
+                    pos += (u32)(total < room ? total : room);
+                }
+            }
+            if (lane == 0) { s_pkpos[gi] = pos; s_pknseg[gi] = nseg; s_pkseglo[gi] = seglo; s_pkex[gi] = ex_lo | (ex_hi << 16); }
+        }
+        __threadfence();
+        bar_named(2, TICK_THREADS);
+    };
+
+    // =============================================================================================
+    // the solver warp
+    // =============================================================================================
+    u32 n_assigned = 0, n_segments = 0;
+    bool seg_overflow = false;
+    if (warp != 0) {
+        for (;;) {
+            bar_named(1, TICK_THREADS);
+            const u32 cmd = s_blk[0];
+            if (cmd == BLK_END) break;
+            block_work(cmd);
+        }
+    } else {
+        const u32 lt_mask = (1u << lane) - 1;
+        for (u32 pass = 0;; ++pass) {
+            u32 seg_base = 0, out_base = 0;
+            bool packed = (a.flags & TF_PACK) == 0;
+            seg_overflow = false;
+            u32 li = 0;
+            while (li < n_list) {
+                // ---- one priority level: entries [li, lj)
+                const u32 lvl = s_gcl[li] >> 16;
+                u32 lj = li + 1;
+                for (;;) {
+                    const u32 e = lj + lane;
+                    const u32 m = __ballot_sync(0xffffffffu, e < n_list && (s_gcl[e] >> 16) == lvl);
+                    if (m == 0xffffffffu) { lj += 32; continue; }
+                    lj += (u32)__ffs(~m) - 1;
+                    break;
+                }
+                const u32 ng = lj - li;
+                bool level_packed = false;
+                if (!packed && !skip_sat && ng <= PACK_MAX_CAND) {
+                    // ---- is this level saturated?  demand (first variant of the tick's order) vs free, exact
+                    //      saturating u64.  Lanes own entries li + lane, li + lane + 32.
+                    u64 dem[RT], cap[RT];
+                    u32 n_cand = 0, has_all = 0;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) { dem[r] = 0; cap[r] = 0; }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const u32 e = li + lane + 32 * j;
+                        if (e < lj) {
+                            const u32 c = s_gcl[e] & 0xFFFFu, n = s_glist[e].y;
+                            const u32 nvv = classes[c].n_variants;
+                            n_cand += nvv;
+                            for (u32 v = 0; v < nvv; ++v) has_all |= classes[c].v[v].all_mask ? 1u : 0u;
+                            const Var& dv = classes[c].v[vorder[c * HQS_MAX_VARIANTS]];
+                            bool servable = true;
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) servable &= (u64)dv.amount[r] <= s_totmax[r];
+                            if (servable) {
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) dem[r] = sat_add64(dem[r], sat_mul64(exact_amount(dv, r), (u64)n));
+                            }
+                        }
+                    }
+                    for (u32 w = lane; w < W; w += 32) {
+                        if (s_excl[w]) continue;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) cap[r] = sat_add64(cap[r], exact_of(s_fr[(size_t)w * RT + r], w, r));
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        n_cand += __shfl_xor_sync(0xffffffffu, n_cand, d);
+                        has_all |= __shfl_xor_sync(0xffffffffu, has_all, d);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            dem[r] = sat_add64(dem[r], __shfl_xor_sync(0xffffffffu, dem[r], d));
+                            cap[r] = sat_add64(cap[r], __shfl_xor_sync(0xffffffffu, cap[r], d));
+                        }
+                    }
+                    if (n_cand <= PACK_MAX_CAND && !has_all) {
+                        // phi = the fraction of the level's demand the pool can serve, when two or more resources are
+                        // over-subscribed (the classes then complement each other and each gets the same fraction of
+                        // its demand this tick); with a single scarce resource any split drains at the same rate
+                        u32 n_sat = 0;
+                        double phi = 1.0;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            if (r < (int)R && cap[r] != HQS_AMOUNT_MAX && dem[r] > cap[r]) n_sat++;
+                        if (n_sat >= 2) {
+#pragma unroll
+                            for (int r = 0; r < RT; ++r)
+                                if (r < (int)R && cap[r] != HQS_AMOUNT_MAX && dem[r] > 0) {
+                                    const double x = __ddiv_rn(__ull2double_rn(cap[r]), __ull2double_rn(dem[r]));
+                                    phi = x < phi ? x : phi;
+                                }
+                        }
+                        if (n_sat != 0) {
+                            if (lane == 0) {
+                                s_blk[0] = BLK_PACK; s_blk[1] = li; s_blk[2] = lj; s_blk[3] = seg_base;
+                                s_blk[4] = (u32)__double2loint(phi); s_blk[5] = (u32)__double2hiint(phi);
+                            }
+                            __syncwarp();
+                            bar_named(1, TICK_THREADS);
+                            block_work(BLK_PACK);
+                            packed = true;
+                            level_packed = s_err == 0;
+                        }
+                    }
+                }
+                // ---- the groups of the level, in order: first-fit (after what pack placed)
+                u32 region_end = seg_base;
+                if (level_packed) {
+                    region_end = seg_base + 2u * W * s_cbase[ng];
+                    if (region_end > SEG_CAP) { seg_overflow = true; }
+                }
+                for (u32 e = li; e < lj; ++e) {
+                    const uint2 ge = s_glist[e];
+                    const u32 g = ge.x, n_all = ge.y;
+                    const u32 c = s_gcl[e] & 0xFFFFu;
+                    const Cls& cl = classes[c];
+                    const u32 nv = cl.n_variants;
+                    u32 remaining = n_all;
+                    u32 seg_lo = seg_base, seg_cur = seg_base;
+                    if (level_packed) {
+                        seg_lo = s_pkseglo[e - li];
+                        seg_cur = seg_lo + s_pknseg[e - li];
+                        remaining = n_all - s_pkpos[e - li];
+                        // hand back what the workers took beyond the class count (tiles [ex_lo, ex_hi))
+                        const u32 ex_lo = s_pkex[e - li] & 0xFFFFu, ex_hi = s_pkex[e - li] >> 16;
+                        if (ex_lo < ex_hi) {
+                            for (u32 tile = ex_lo; tile < ex_hi; ++tile) {
+                                const u32 w = tile * 32 + lane;
+                                for (u32 v = 0; v < nv; ++v) {
+                                    const u32 ex = w < W ? __ldcg(a.pk.taken + (size_t)w * PACK_MAX_CAND + s_cbase[e - li] + v) : 0;
+                                    if (!ex) continue;
+                                    const Var& dv = cl.v[v];
+#pragma unroll
+                                    for (int r = 0; r < RT; ++r)
+                                        if (((dv.used_mask >> r) & 1) && s_fr[(size_t)w * RT + r] != AMAX)
+                                            s_fr[(size_t)w * RT + r] += (AT)((u64)ex * dv.amount[r]);
+                                }
+                            }
+                            // free amounts grew: no frontier may lie beyond the first tile that got something back
+                            for (u32 c2 = lane; c2 < Q; c2 += 32)
+                                if (s_front[c2] > ex_lo) s_front[c2] = (unsigned short)ex_lo;
+                            __syncwarp();
+                        }
+                    }
+                    for (u32 vi = 0; vi < nv && remaining; ++vi) {
+                        // Each worker offers the untried variant that costs the smallest share of what it has left:
+                        // min over variants of max_r f32(amount_r) * (1 / f32(free_r)), `All` = +inf, ties to the lower
+                        // variant id (specification: tests/greedy_model.py::_Tick.next_variant).
+                        const bool last_round = vi + 1 == nv;
+                        bool front = true;
+                        for (u32 tile = s_front[c]; tile < n_tiles && remaining; ++tile) {
+                            const u32 w = tile * 32 + lane;
+                            const bool in_pool = w < W;
+                            const bool has = in_pool && !s_excl[w];
+                            AT fr[RT];
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) fr[r] = in_pool ? s_fr[(size_t)w * RT + r] : 0;
+                            const u32 unt = in_pool ? s_unt[w] : 0;
+                            u32 v = 0, td = 0;
+                            if (nv > 1) {
+                                td = (vi && in_pool) ? s_td[w] : 0;
+                                float inv[RT];
+#pragma unroll
+                                for (int r = 0; r < RT; ++r)
+                                    inv[r] = __fdiv_rn(1.0f, __double2float_rn(__ull2double_rn(in_pool ? exact_of(fr[r], w, r) : 0)));
+                                float best_d = 0.0f;
+                                int best_v = -1;
+                                for (u32 vv = 0; vv < nv; ++vv) {
+                                    if ((td >> vv) & 1) continue;
+                                    const Var& cv = cl.v[vv];
+                                    float dom = 0.0f;
+                                    if (cv.all_mask) dom = __int_as_float(0x7f800000);
+                                    else {
+#pragma unroll
+                                        for (int r = 0; r < RT; ++r) {
+                                            if (!((cv.used_mask >> r) & 1) || fr[r] == AMAX) continue;
+                                            const float x = __fmul_rn(cv.rcpf[RT + r], inv[r]);
+                                            dom = x > dom ? x : dom;
+                                        }
+                                    }
+                                    if (best_v < 0 || dom < best_d) { best_v = (int)vv; best_d = dom; }
+                                }
+                                v = (u32)best_v;
+                            }
+                            const Var& dv = cl.v[v];
+                            u64 cnt = 0;
+                            if (has) {
+                                const uint8_t blk = blocked ? blocked[(size_t)w * Q + c] : 0;
+                                const u64 rt = a.any_time_limit ? s_remtime[w] : HQS_TIME_INF;
+                                if (admissible(dv, v, blk, rt)) cnt = fit_count<RT>(fr, unt, dv, remaining);
+                            }
+                            // ---- hand out `remaining` in worker order: the first worker that can take anything often
+                            //      takes it all (mode M1); otherwise an inclusive scan over the tile
+                            const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
+                            u32 take = 0, exc = 0, handed = 0;
+                            if (hasm) {
+                                const u32 first = (u32)__ffs(hasm) - 1;
+                                const u32 fall = __shfl_sync(0xffffffffu, cnt >= remaining ? 1u : 0u, first);
+                                if (fall) {
+                                    take = lane == first ? remaining : 0;
+                                    handed = remaining;
+                                } else if (remaining <= 0x03FFFFFFu) {
+                                    u32 inc = (u32)cnt;
+#pragma unroll
+                                    for (int d = 1; d < 32; d <<= 1) {
+                                        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                        if ((int)lane >= d) inc += y;
+                                    }
+                                    exc = inc - (u32)cnt;
+                                    if (cnt && exc < remaining) take = min((u32)cnt, remaining - exc);
+                                    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+                                    handed = min(total, remaining);
+                                } else {
+                                    u64 inc = cnt;
+#pragma unroll
+                                    for (int d = 1; d < 32; d <<= 1) {
+                                        const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                        if ((int)lane >= d) inc += y;
+                                    }
+                                    const u64 e64 = inc - cnt;
+                                    exc = (u32)(e64 < remaining ? e64 : remaining);
+                                    if (cnt && e64 < remaining) take = (u32)(cnt < remaining - e64 ? cnt : remaining - e64);
+                                    const u64 total = __shfl_sync(0xffffffffu, inc, 31);
+                                    handed = (u32)(total < remaining ? total : remaining);
+                                }
+                            }
+                            const u32 tkm = __ballot_sync(0xffffffffu, take != 0);
+                            if (take) {
+                                const u32 si = seg_cur + __popc(tkm & lt_mask);
+                                if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w | (v << 16); }
+                                take_from<RT, AT>(fr, dv, take);
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) s_fr[(size_t)w * RT + r] = fr[r];
+                                // touched resources are no longer "untouched" (free == total); an unbounded amount stays as it is
+                                u32 touched = dv.all_mask & dv.used_mask;
+#pragma unroll
+                                for (int r = 0; r < RT; ++r)
+                                    if (((dv.used_mask >> r) & 1) && !((dv.all_mask >> r) & 1) && fr[r] != AMAX) touched |= 1u << r;
+                                s_unt[w] = unt & ~touched;
+                                if constexpr (NARROW) {
+                                    // `All` consumed the whole resource: the exact free amount is 0, remainder included
+                                    const u32 z = dv.all_mask & dv.used_mask;
+                                    if (z) {
+#pragma unroll
+                                        for (int r = 0; r < RT; ++r)
+                                            if ((z >> r) & 1) p_rem[(size_t)w * RT + r] = 0;
+                                    }
+                                }
+                            }
+                            seg_cur += __popc(tkm);
+                            // ---- frontier: a worker whose fit count was not capped by `remaining` and that took all of it
+                            //      has no room left for this variant; free amounts only shrink during first-fit
+                            const bool dead_v = cnt < remaining && take == (u32)cnt;
+                            bool lane_dead;
+                            if (nv > 1) {
+                                td |= (1u << v) | (dead_v ? (0x100u << v) : 0u);
+                                if (in_pool) s_td[w] = (unsigned short)td;
+                                lane_dead = last_round && (td >> 8) == ((1u << nv) - 1u);
+                            } else {
+                                lane_dead = dead_v;
+                            }
+                            if (front) {
+                                const u32 alive = __ballot_sync(0xffffffffu, in_pool && !lane_dead);
+                                if (alive == 0 && last_round) { if (lane == 0) s_front[c] = (unsigned short)(tile + 1); }
+                                else front = false;
+                            }
+                            remaining -= handed;
+                            __syncwarp();
+                        }
+                    }
+                    const u32 k = n_all - remaining;
+                    // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
+                    u32 k_loc = k;
+                    if (before) {
+                        const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
+                        const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
+                        k_loc = k > bef ? k - bef : 0;
+                        k_loc = k_loc < loc ? k_loc : loc;
+                    }
+                    if (lane == 0) {
+                        GroupOut go;
+                        go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_cur - seg_lo;
+                        a.gout[g] = go;
+                    }
+                    out_base += k_loc;
+                    if (!level_packed) {
+                        seg_base = seg_cur;
+                        if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+                    }
+                }
+                if (level_packed) seg_base = region_end > SEG_CAP ? SEG_CAP : region_end;
+                li = lj;
+            }
+            n_assigned = out_base;
+            n_segments = seg_base;
+            // ---- min-utilisation (solver.rs:154-156, 479-518): a worker either receives at least
+            //      min_cpus = total * (mu - 1) + free cpus of new work in this tick, or nothing.  The MILP has a boolean
+            //      per worker; here a violating worker is taken out of the tick and the solve starts over, so its tasks
+            //      go to the other workers (or stay ready).
+            if (!a.min_util || pass + 1 >= MU_MAX_PASSES) break;
+            u32 viol = 0;
+            for (u32 w = lane; w < W; w += 32) {
+                if (s_excl[w]) continue;
+                const float muf = a.min_util[w];
+                const u64 t0 = a.total_rw[(size_t)w * R], f0 = a.free_rw[(size_t)w * R];
+                if (!(muf > 0.001f) || t0 == HQS_AMOUNT_MAX || f0 == HQS_AMOUNT_MAX) continue;
+                const double mu = (double)muf;
+                const double cpu_total = __ddiv_rn(__ull2double_rn(t0), 10000.0), cpu_free = __ddiv_rn(__ull2double_rn(f0), 10000.0);
+                const double min_cpus = __dadd_rn(__dmul_rn(cpu_total, __dsub_rn(mu, 1.0)), cpu_free);
+                const u64 fa = exact_of(s_fr[(size_t)w * RT + 0], w, 0);
+                const double new_cpus = __ddiv_rn(__ull2double_rn(f0 - fa), 10000.0);
+                if (min_cpus >= 0.0001 && new_cpus > 0.0 && new_cpus < __dsub_rn(min_cpus, 1e-9)) { s_excl[w] = 1; viol = 1; }
+            }
+            if (!__any_sync(0xffffffffu, viol)) break;
+            // every listed group rewrites its record in the next pass
+            if (lane == 0) s_blk[0] = BLK_RESTART;
+            __syncwarp();
+            bar_named(1, TICK_THREADS);
+            block_work(BLK_RESTART);
+        }
+        if (lane == 0) s_blk[0] = BLK_END;
+        __syncwarp();
+        // ---- release the worker CTAs as early as possible: they need the group records, the segments and n_segments
+        u32 err = s_err ? 2u : (seg_overflow ? 1u : 0u);
+        if (!err && n_assigned > a.out_cap && (a.flags & TF_EMIT)) err = 3u;
+        if (lane == 0) {
+            a.hdr->n_segments = n_segments;
+            a.hdr->n_assigned = n_assigned;
+            a.hdr->error = err;
+            __threadfence();
+            const u32 seq = s_npacks + 1;
+            st_release(&a.sync->cmd, (seq << 2) | ((err == 0 && (a.flags & TF_EMIT)) ? CMD_EMIT : CMD_EXIT));
+            s_final_err = err;
+        }
+        __syncwarp();
+        bar_named(1, TICK_THREADS);
+    }
+    // ---- epilogue (all warps): free vectors after the tick, header, reset of the per-tick counters
+    const long long t_solved = clock64();
+    __syncthreads();
+    for (u32 w = tid; w < W; w += blockDim.x) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (r < (int)R) {
+                const u64 x = exact_of(s_fr[(size_t)w * RT + r], w, r);
+                a.free_after[(size_t)w * R + r] = x;
+                if (a.hdr_host) reinterpret_cast<u64*>(a.hdr_host + 1)[(size_t)w * R + r] = x;
+            }
+    }
+    if (tid == 0) {
+        if (!spin_until_ge(&a.sync->emit_done, nW)) s_err = 2;
+    }
+    __syncthreads();
+    const long long t_end = clock64();
+    for (u32 g = tid; g < G; g += blockDim.x) a.total_local[g] = 0;
+    if (tid == 0) {
+        u32 err = s_final_err;
+        const u32 werr = __ldcg(&a.sync->error);
+        if (!err && (s_err || werr)) err = 2u;
+        TickHeaderOut h;
+        h.n_assigned = warp == 0 ? n_assigned : 0;
+        h.n_groups = n_list;
+        h.n_segments = n_segments;
+        h.error = err;
+        h.dbg[0] = (unsigned long long)(t_counted - t_start);     // staging + wait for the histogram
+        h.dbg[1] = (unsigned long long)(t_prologue - t_counted);  // exchange + compaction + demand
+        h.dbg[2] = (unsigned long long)(t_solved - t_prologue);   // the solver warp
+        h.dbg[3] = (unsigned long long)(t_end - t_solved);        // emit (+ free vectors)
+        h.dbg[4] = n_list;
+        h.dbg[5] = (unsigned long long)(t_end - t_start);
+        h.dbg[6] = global_timer_ns() - gt_start;                  // the same interval in ns
+        h.dbg[7] = s_npacks;
+        *a.hdr = h;
+        if (a.hdr_host) *a.hdr_host = h;
+        // the tick is over: every worker CTA has left its loops
+        a.sync->cmd = 0; a.sync->count_done = 0; a.sync->scan_done = 0; a.sync->pack_done = 0; a.sync->emit_done = 0;
+        a.sync->error = 0;
+        __threadfence_system();
+    }
+}
+
+template <int RT, typename AT>
+__global__ void __launch_bounds__(TICK_THREADS, 1) tick_k(const __grid_constant__ TickArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    if (blockIdx.x == 0) solver_cta<RT, AT>(a, smem_dyn);
+    else worker_cta<RT>(a, smem_dyn);
+}
+
+// standalone histogram (NCCL variant of the sharded tick: the host all-gathers the totals between the two halves)
+__global__ void __launch_bounds__(TICK_THREADS) count_only_k(const __grid_constant__ TickArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    for (u32 b = blockIdx.x; b < a.P; b += gridDim.x) count_chunk(a, b, reinterpret_cast<u32*>(smem_dyn));
+}
+
+// per-worker totals of the count segments (what-if query)
+__global__ void seg_worker_totals_k(const GroupOut* __restrict__ gout, u32 G, const u32* __restrict__ seg_cum,
+                                    const u32* __restrict__ seg_wv, u32* __restrict__ per_worker) {
+    // one thread per group: walks the group's segments (inclusive end ranks -> counts)
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const GroupOut go = gout[g];
+    if (go.k == 0) return;
+    u32 prev = 0;
+    for (u32 i = 0; i < go.seg_n; ++i) {
+        const u32 end = seg_cum[go.seg_lo + i];
+        atomicAdd(&per_worker[seg_wv[go.seg_lo + i] & 0xFFFFu], end - prev);
+        prev = end;
+    }
+}

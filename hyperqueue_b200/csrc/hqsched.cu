@@ -15,18 +15,17 @@
 //   key[h]   u32  bit31 READY | bit30 DONE (assigned by a tick) | bit29 VALID | level(15) | class(14)
 //   prio[h]  u64  tako Priority (only read when the level table changes)
 //   deps[h]  u32  unfinished dependencies (DAG mode), cons_off/cons: CSR of consumers
-// One tick = 3 kernels on one stream:
-//   count_k : per-chunk histogram of ready tasks by group g = level*Q + class   (HBM streaming, 4 B/task)
-//   solve_k : CTA 0: sequential first-fit over non-empty groups, one thread per worker (worker state in
-//             registers; amounts gcd-scaled to 32 bits when the tick allows it, else 64-bit);
-//             CTAs 1..: exclusive scan of the per-chunk histograms over chunks (runs concurrently), then they
-//             stand by: when CTA 0 finds the first saturated priority level it hands every worker to one warp
-//             of those CTAs, which fills it independently (pack_body) and reports back;
-//   emit_k  : stable rank of every ready task inside its group, rank -> (worker, variant) through
-//             the solver's count segments, compact write of 8-byte assignments, READY -> DONE
-// Sharded over several GPUs (one context per GPU, tasks block-sharded, workers replicated) a fourth kernel,
-// xchg_k, stores the rank's count vector into every peer's exchange buffer over NVLink between count_k and
-// solve_k; solve_k acquires the peers' flags and sums the vectors itself (no host collective).
+// One tick = ONE cooperative kernel (tick_k, hqs_tick.cuh):
+//   worker CTAs : per-chunk histogram of ready tasks by group g = level*Q + class (HBM streaming, 4 B/task), exclusive
+//                 scan of the chunk table over chunks, on request the pack step (one warp fills one worker), then the
+//                 stable rank of every ready task inside its group, rank -> (worker, variant) through the solver's count
+//                 segments, compact write of 8-byte assignments, READY -> DONE
+//   solver CTA  : stages the worker state in shared memory (read straight from the pinned host buffer while the others
+//                 count), then one warp walks the non-empty groups in priority order: sparse first-fit over tiles of 32
+//                 workers starting at the class's frontier tile (amounts gcd-scaled to 32 bits when the tick allows it)
+// Sharded over several GPUs (one context per GPU, tasks block-sharded, workers replicated) the solver CTA stores the
+// rank's count vector into every peer's exchange buffer over NVLink and acquires the peers' flags before it solves (no
+// host collective).
 // The algorithm has a sequential specification, tests/greedy_model.py, which the kernels equal bit for bit.
 #include "../../include/hqsched.h"
 
@@ -50,7 +49,7 @@ typedef uint64_t u64;
 
 #include "hqs_ready_set.cuh"
 #include "hqs_solver.cuh"
-#include "hqs_emit.cuh"
+#include "hqs_tick.cuh"
 
 
 // ================================================================================================
@@ -108,30 +107,38 @@ struct hqs_ctx {
     u32* d_newcnt = nullptr; u64* d_newprio = nullptr;
     // tick buffers
     u32 sm_count = 148;
+    u32 grid_ctas = 148;                // CTAs of the cooperative tick kernel (solver CTA + worker CTAs)
     u32 G_cap = 0, P_cap = 0;
     u32* d_table = nullptr;
     u32* d_total = nullptr;
     GroupOut* d_gout = nullptr;
-    uint2* d_glist = nullptr;
-    SolveSync* d_sync = nullptr;
+    TickSync* d_sync = nullptr;
+    size_t smem_budget[2] = {0, 0};     // dynamic shared memory a tick kernel instance may use (narrow, wide)
+    bool sync_dirty = true;             // the counters must be zeroed before the next launch (first tick / after a failed one)
     u64* d_pk_fr = nullptr; u32* d_pk_quota = nullptr; u32* d_pk_taken = nullptr; u32* d_pk_cand = nullptr; u32* d_pk_meta = nullptr;
+    u32* d_rem_scratch = nullptr; uint8_t* d_excl = nullptr;
     u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr;
     hqs_assignment* d_out = nullptr; u32 out_cap_dev = 0;
     TickHeaderOut* d_hdr = nullptr;
     u64* d_free_after = nullptr;
-    unsigned char* d_tickin = nullptr; size_t tickin_cap = 0;
-    unsigned char* h_tickin = nullptr;  // pinned
-    unsigned char* h_hdr = nullptr;     // pinned: TickHeaderOut + free_after
+    unsigned char* d_tickin = nullptr; size_t tickin_cap = 0;   // device copy of the tick input (blocked mask; everything when zero-copy is off)
+    unsigned char* h_tickin = nullptr;  // pinned + mapped: the solver CTA reads the worker state from here
+    unsigned char* h_tickin_dev = nullptr;   // device-side address of h_tickin
+    bool zero_copy = true;
+    unsigned char* h_hdr = nullptr;     // pinned + mapped: TickHeaderOut + free_after, written by the kernel
+    unsigned char* h_hdr_dev = nullptr;
     size_t h_hdr_cap = 0;
     u32* h_small = nullptr;             // pinned scratch (counters)
     // last tick
     u32 last_W = 0, last_G = 0, last_L = 0;
+    bool last_blocked = false;
     bool tick_pending = false;
     bool own_stream = true;
     bool profile = false;
     bool pack = true;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    float last_ms[4] = {0, 0, 0, 0};
     hqs_stats stats{};
     unsigned long long dbg[8] = {0};
 };
@@ -266,7 +273,7 @@ void distinct_priorities(const u64* p, u32 n, std::vector<u64>& out) {
 }
 
 int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
-    if (G > ctx->G_cap || P > ctx->P_cap) {
+    if (G > ctx->G_cap || P > ctx->P_cap || (size_t)G * P > (size_t)ctx->G_cap * ctx->P_cap) {
         const u32 ng = std::max(G, ctx->G_cap), np = std::max(P, ctx->P_cap);
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_table) CU(cudaFree(ctx->d_table));
@@ -274,12 +281,10 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
         if (ng > ctx->G_cap) {
             if (ctx->d_total) CU(cudaFree(ctx->d_total));
             if (ctx->d_gout) CU(cudaFree(ctx->d_gout));
-            if (ctx->d_glist) CU(cudaFree(ctx->d_glist));
             CU(cudaMalloc(&ctx->d_total, ng * sizeof(u32)));
             CU(cudaMemsetAsync(ctx->d_total, 0, ng * sizeof(u32), ctx->stream));
             CU(cudaMalloc(&ctx->d_gout, ng * sizeof(GroupOut)));
             CU(cudaMemsetAsync(ctx->d_gout, 0, ng * sizeof(GroupOut), ctx->stream));
-            CU(cudaMalloc(&ctx->d_glist, ng * sizeof(uint2)));
         }
         ctx->G_cap = ng; ctx->P_cap = np;
     }
@@ -288,12 +293,21 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
         CU(cudaMalloc(&ctx->d_seg_wv, SEG_CAP * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_hdr, sizeof(TickHeaderOut)));
         CU(cudaMalloc(&ctx->d_free_after, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
-        CU(cudaMalloc(&ctx->d_sync, sizeof(SolveSync)));
+        CU(cudaMalloc(&ctx->d_sync, sizeof(TickSync)));
         CU(cudaMalloc(&ctx->d_pk_fr, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
         CU(cudaMalloc(&ctx->d_pk_quota, (size_t)HQS_MAX_WORKERS * PACK_MAX_CAND * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_pk_taken, (size_t)HQS_MAX_WORKERS * PACK_MAX_CAND * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_pk_cand, PACK_MAX_CAND * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_pk_meta, 2 * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_rem_scratch, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
+        CU(cudaMalloc(&ctx->d_excl, HQS_MAX_WORKERS));
+        ctx->sync_dirty = true;
+    }
+    if (!ctx->h_hdr) {
+        ctx->h_hdr_cap = sizeof(TickHeaderOut) + (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * 8;
+        CU(cudaHostAlloc(&ctx->h_hdr, ctx->h_hdr_cap, cudaHostAllocMapped));
+        memset(ctx->h_hdr, 0, ctx->h_hdr_cap);
+        CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_hdr_dev), ctx->h_hdr, 0));
     }
     if (out_cap > ctx->out_cap_dev) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -306,7 +320,7 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
 }
 
 struct TickLayout {
-    size_t off_free, off_total, off_rem, off_order, off_vorder, off_blocked, bytes;
+    size_t off_free, off_total, off_rem, off_order, off_vorder, off_mu, off_blocked, bytes;
 };
 
 TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
@@ -316,6 +330,7 @@ TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
     l.off_total = o; o += (size_t)W * R * 8;
     l.off_rem = o; o += (size_t)W * 8;
     l.off_order = o; o += (size_t)Q * 4;
+    l.off_mu = o; o += (size_t)W * 4;
     l.off_vorder = o; o += (size_t)Q * HQS_MAX_VARIANTS;
     o = (o + 15) & ~size_t(15);
     l.off_blocked = o; if (blocked) o += (size_t)W * Q;
@@ -374,7 +389,10 @@ void tick_orders(const hqs_ctx* ctx, u32 W, const u64* free_rw, const u64* total
     for (u32 c = 0; c < Q; ++c) order[c] = sc[c].second;
 }
 
-struct TickGeom { u32 G, L, P, chunk, emit_warps, g_smem, nbits; size_t emit_smem; };
+// Chunk geometry of the streaming steps: every worker CTA of the tick kernel owns chunks b, b + nW, ...; an emit warp owns
+// `rows` rows of 32 consecutive tasks of its chunk.  rows is chosen so that the table splits into (about) one chunk per
+// worker CTA; large tables take several chunks per CTA.
+struct TickGeom { u32 G, L, P, chunk, rows, emit_warps, g_smem, nbits; size_t worker_smem; };
 
 TickGeom tick_geom(const hqs_ctx* ctx) {
     TickGeom t;
@@ -382,34 +400,45 @@ TickGeom tick_geom(const hqs_ctx* ctx) {
     t.G = t.L * std::max<u32>(ctx->Q, 1);
     t.nbits = 1;
     while ((1u << t.nbits) < t.G) t.nbits++;
-    // emit_k shared memory: warps * G counters (+ G solver records + the segment cache); as many warps per
-    // CTA as the budget allows, two CTAs per SM
+    // emit step shared memory: warps * G counters (+ G solver records) + the segment cache
     const size_t seg_cache = 2 * EMIT_SEG_SMEM * sizeof(u32);
-    t.emit_warps = 8;
-    for (u32 ew : {32u, 16u}) {
-        if ((size_t)ew * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= 64 * 1024) { t.emit_warps = ew; break; }
-    }
-    t.g_smem = ((size_t)t.emit_warps * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= EMIT_SMEM_BUDGET) ? 1 : 0;
-    t.emit_smem = (size_t)t.emit_warps * t.G * 4 + (t.g_smem ? (size_t)t.G * sizeof(GroupOut) : 0) + seg_cache;
+    t.emit_warps = TICK_WARPS;
+    while (t.emit_warps > 1 && (size_t)t.emit_warps * t.G * 4 > 128 * 1024) t.emit_warps /= 2;
+    t.g_smem = ((size_t)t.emit_warps * t.G * 4 + (size_t)t.G * sizeof(GroupOut) + seg_cache <= 192 * 1024) ? 1 : 0;
+    const size_t emit_smem = (size_t)t.emit_warps * t.G * 4 + (t.g_smem ? (size_t)t.G * sizeof(GroupOut) : 0) + seg_cache;
+    const size_t pack_smem = (size_t)TICK_WARPS * PACK_MAX_CAND * sizeof(double);
+    t.worker_smem = std::max(std::max(emit_smem, pack_smem), (size_t)t.G * 4);
     const u32 n = std::max<u32>(ctx->n_handles, 1);
-    const u32 chunk = t.emit_warps * 32 * EMIT_ROWS;     // every emit warp owns EMIT_ROWS rows
-    t.chunk = chunk;
-    t.P = (n + chunk - 1) / chunk;
+    const u32 nW = std::max<u32>(ctx->grid_ctas - 1, 1);
+    const u32 per_row = t.emit_warps * 32;
+    t.rows = std::min<u32>(EMIT_ROWS_MAX, std::max<u32>(1, (u32)(((u64)n + (u64)nW * per_row - 1) / ((u64)nW * per_row))));
+    t.chunk = per_row * t.rows;
+    t.P = (n + t.chunk - 1) / t.chunk;
     return t;
 }
 
+int ensure_tickin(hqs_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->tickin_cap) return HQS_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_tickin) CU(cudaFree(ctx->d_tickin));
+    if (ctx->h_tickin) CU(cudaFreeHost(ctx->h_tickin));
+    ctx->d_tickin = nullptr; ctx->h_tickin = nullptr;
+    ctx->tickin_cap = bytes * 2;
+    CU(cudaMalloc(&ctx->d_tickin, ctx->tickin_cap));
+    CU(cudaHostAlloc(&ctx->h_tickin, ctx->tickin_cap, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_tickin_dev), ctx->h_tickin, 0));
+    return HQS_OK;
+}
+
+// Fills the pinned staging buffer with the tick's worker state and orders.  The solver CTA reads it in place (mapped
+// host memory, overlapped with the histogram of the worker CTAs); only the blocked mask, which the pack warps read
+// with scattered byte loads, is copied to the device.
 int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw,
-                      const uint8_t* blocked, TickLayout* lay_out) {
+                      const uint8_t* blocked, TickLayout* lay_out, bool* has_mu, bool* any_time) {
     const u32 R = ctx->R, Q = ctx->Q;
     const TickLayout lay = tick_layout(W, R, Q, blocked != nullptr);
-    if (lay.bytes > ctx->tickin_cap) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_tickin) CU(cudaFree(ctx->d_tickin));
-        if (ctx->h_tickin) CU(cudaFreeHost(ctx->h_tickin));
-        ctx->tickin_cap = lay.bytes * 2;
-        CU(cudaMalloc(&ctx->d_tickin, ctx->tickin_cap));
-        CU(cudaMallocHost(&ctx->h_tickin, ctx->tickin_cap));
-    }
+    int rc = ensure_tickin(ctx, lay.bytes);
+    if (rc) return rc;
     unsigned char* h = ctx->h_tickin;
     memcpy(h + lay.off_free, free_rw, (size_t)W * R * 8);
     memcpy(h + lay.off_total, total_rw, (size_t)W * R * 8);
@@ -428,14 +457,36 @@ int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64*
     ctx->tick_narrow = narrow;
     ctx->stats.narrow_amounts = narrow ? 1 : 0;
     u64* rem = reinterpret_cast<u64*>(h + lay.off_rem);
-    for (u32 w = 0; w < W; ++w) rem[w] = workers[w].remaining_time_ms;
+    float* mu = reinterpret_cast<float*>(h + lay.off_mu);
+    bool mu_any = false, time_any = false;
+    for (u32 w = 0; w < W; ++w) {
+        rem[w] = workers[w].remaining_time_ms;
+        time_any |= rem[w] != HQS_TIME_INF;
+        mu[w] = workers[w].min_utilization;
+        mu_any |= mu[w] > 0.001f;
+    }
     tick_orders(ctx, W, free_rw, total_rw, reinterpret_cast<u32*>(h + lay.off_order), h + lay.off_vorder);
     if (blocked) {
         // ABI bit index ((w*Q + c) * HQS_MAX_VARIANTS + v) with HQS_MAX_VARIANTS == 8: one byte per (w, c)
         memcpy(h + lay.off_blocked, blocked, (size_t)W * Q);
     }
-    CU(cudaMemcpyAsync(ctx->d_tickin, h, lay.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->zero_copy) CU(cudaMemcpyAsync(ctx->d_tickin, h, lay.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else if (blocked) CU(cudaMemcpyAsync(ctx->d_tickin + lay.off_blocked, h + lay.off_blocked, (size_t)W * Q, cudaMemcpyHostToDevice, ctx->stream));
     *lay_out = lay;
+    *has_mu = mu_any;
+    *any_time = time_any;
+    ctx->h_small[9] = mu_any ? 1u : 0u;
+    ctx->h_small[10] = time_any ? 1u : 0u;
+    return HQS_OK;
+}
+
+int validate_workers(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw) {
+    if (!workers || !free_rw || !total_rw) return fail(ctx, HQS_E_INVALID, "null worker arrays");
+    if (W == 0 || W > HQS_MAX_WORKERS) return fail(ctx, HQS_E_LIMIT, "n_workers=%u outside 1..%u", W, HQS_MAX_WORKERS);
+    for (u32 w = 1; w < W; ++w)
+        if (workers[w].worker_id <= workers[w - 1].worker_id)
+            return fail(ctx, HQS_E_INVALID, "workers must be sorted by ascending unique worker_id");
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
     return HQS_OK;
 }
 
@@ -457,106 +508,136 @@ void max_of_u32_pair(const u32* a, const u32* b, u32 n, u32* max_a, u32* max_b) 
     *max_b = mb[0];
 }
 
-int validate_workers(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw) {
-    if (!workers || !free_rw || !total_rw) return fail(ctx, HQS_E_INVALID, "null worker arrays");
-    if (W == 0 || W > HQS_MAX_WORKERS) return fail(ctx, HQS_E_LIMIT, "n_workers=%u outside 1..%u", W, HQS_MAX_WORKERS);
-    for (u32 w = 1; w < W; ++w)
-        if (workers[w].worker_id <= workers[w - 1].worker_id)
-            return fail(ctx, HQS_E_INVALID, "workers must be sorted by ascending unique worker_id");
-    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
-    return HQS_OK;
+const void* tick_fn(u32 RT, bool narrow) {
+#define HQS_PICK(AT) (RT == 4 ? (const void*)tick_k<4, AT> : RT == 8 ? (const void*)tick_k<8, AT> : (const void*)tick_k<16, AT>)
+    return narrow ? HQS_PICK(u32) : HQS_PICK(u64);
+#undef HQS_PICK
 }
 
-int launch_count(hqs_ctx* ctx, const TickGeom& t) {
-    ctx->ev_valid = false;
-    if (ctx->profile) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    count_k<<<t.P, COUNT_THREADS, t.G * sizeof(u32), ctx->stream>>>(ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G,
-                                                                   ctx->d_table, ctx->d_total);
-    ctx->stats.kernel_launches++;
-    CU(cudaGetLastError());
-    if (ctx->profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    return HQS_OK;
-}
-
-int launch_solve_emit(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, bool blocked,
-                      const u32* d_counts_all, const u32* d_before, u32 out_cap, bool no_emit = false) {
-    SolveArgs a;
-    a.free_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_free);
-    a.total_rw = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_total);
-    a.rem_time = reinterpret_cast<const u64*>(ctx->d_tickin + lay.off_rem);
-    a.order = reinterpret_cast<const u32*>(ctx->d_tickin + lay.off_order);
-    a.vorder = ctx->d_tickin + lay.off_vorder;
+TickArgs base_args(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, bool blocked) {
+    TickArgs a;
+    memset(&a, 0, sizeof a);
+    const unsigned char* in = ctx->zero_copy ? ctx->h_tickin_dev : ctx->d_tickin;
+    a.free_rw = reinterpret_cast<const u64*>(in + lay.off_free);
+    a.total_rw = reinterpret_cast<const u64*>(in + lay.off_total);
+    a.rem_time = reinterpret_cast<const u64*>(in + lay.off_rem);
+    a.order = reinterpret_cast<const u32*>(in + lay.off_order);
+    a.vorder = in + lay.off_vorder;
     a.blocked = blocked ? ctx->d_tickin + lay.off_blocked : nullptr;
+    a.min_util = ctx->h_small[9] ? reinterpret_cast<const float*>(in + lay.off_mu) : nullptr;
+    a.any_time_limit = ctx->h_small[10];
     const bool narrow = ctx->tick_narrow;
     a.classes = narrow ? ctx->d_classes32 : ctx->d_classes;
     a.classes64 = ctx->d_classes;
     for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) a.gscale[r] = ctx->gscale[r] ? ctx->gscale[r] : 1;
     a.W = W; a.Q = ctx->Q; a.L = t.L; a.R = ctx->R; a.G = t.G;
     a.classes_bytes = ctx->Q * (narrow ? ctx->class_bytes32 : ctx->class_bytes);
+    a.key = ctx->d_key; a.n_handles = ctx->n_handles; a.chunk = t.chunk; a.rows = t.rows; a.P = t.P; a.nbits = t.nbits;
+    a.emit_warps = t.emit_warps; a.g_smem = t.g_smem;
     a.total_local = ctx->d_total;
-    a.total_all = d_counts_all ? d_counts_all : ctx->d_total;
-    a.before = d_before;
+    a.table = ctx->d_table;
     a.gout = ctx->d_gout;
     a.seg_cum = ctx->d_seg_cum; a.seg_wv = ctx->d_seg_wv;
     a.free_after = ctx->d_free_after;
     a.hdr = ctx->d_hdr;
-    a.glist = ctx->d_glist;
-    a.table = ctx->d_table; a.P = t.P;
-    a.x_world = 0; a.x_rank = 0; a.x_seq = 0; a.x_counts = nullptr; a.x_flags = nullptr; a.x_all = nullptr; a.x_before = nullptr;
-    if (ctx->x_tick) {
-        const u32 parity = ctx->x_seq & 1u;
-        a.x_world = ctx->x_world; a.x_rank = ctx->x_rank; a.x_seq = ctx->x_seq;
-        a.x_counts = ctx->d_xbuf + (size_t)parity * HQS_MAX_PEERS * HQS_MAX_GROUPS;
-        a.x_flags = ctx->d_xbuf + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
-        a.x_all = ctx->d_xall; a.x_before = ctx->d_xbefore;
-    }
+    a.hdr_host = reinterpret_cast<TickHeaderOut*>(ctx->h_hdr_dev);
+    a.out = ctx->d_out;
+    a.rem_scratch = ctx->d_rem_scratch;
     a.sync = ctx->d_sync;
     a.pk.fr = ctx->d_pk_fr; a.pk.quota = ctx->d_pk_quota; a.pk.taken = ctx->d_pk_taken;
     a.pk.cand = ctx->d_pk_cand; a.pk.meta = ctx->d_pk_meta;
-    const u32 threads = std::max<u32>(128, (W + 31) / 32 * 32);
-    const u32 nw = threads / 32;
-    a.scan_ctas = std::min<u32>((t.G + nw - 1) / nw, ctx->sm_count - 1);
-    // grid: CTA 0 solves; the others scan the chunk table and then stand by to fill workers (one warp per
-    // worker, spread over the SMs).  All CTAs must be co-resident (cooperative launch): <= one per SM.
-    u32 grid = std::max<u32>(1 + a.scan_ctas, std::min<u32>(ctx->sm_count, 1 + (W + 1) / 2));
-    grid = std::min<u32>(grid, ctx->sm_count);
-    static const bool dbg_small_grid = getenv("HQS_DEBUG_SMALL_GRID") != nullptr;   // profiling aid: solver CTA + scan CTAs only
-    if (dbg_small_grid) grid = 1 + a.scan_ctas;
-    a.pack_enabled = (ctx->pack && grid >= 2 && !dbg_small_grid) ? 1 : 0;
-    // SMALL variant: class table + variant order staged in shared memory
-    a.smem_classes = ((size_t)a.classes_bytes + (size_t)ctx->Q * HQS_MAX_VARIANTS <= 48 * 1024) ? 1 : 0;
-    a.smem_vorder = a.smem_classes;
-    size_t solve_smem = 0;
-    if (a.smem_classes) solve_smem += ((a.classes_bytes + 15u) & ~15u) + ((ctx->Q * HQS_MAX_VARIANTS + 15u) & ~15u);
-    a.smem_glist_cap = std::min<u32>(t.G, 2048);
-    solve_smem += (size_t)a.smem_glist_cap * (sizeof(uint2) + sizeof(u32) + 1) + (size_t)((a.smem_glist_cap + 31) / 32) * 4 + 32;
-    solve_smem += (size_t)a.smem_glist_cap * sizeof(GroupOut) + 2 * SEG_SMEM * sizeof(u32);
-    solve_smem = std::max(solve_smem, (size_t)nw * PACK_MAX_CAND * sizeof(double));     // pack warps' scratch
-    CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(SolveSync), ctx->stream));
+    a.excl_glob = ctx->d_excl;
+    return a;
+}
+
+// shared-memory layout of the solver CTA: mandatory arrays first, then the optional ones while they fit
+size_t solver_layout(const hqs_ctx* ctx, TickArgs& a, size_t budget, bool sharded) {
+    const u32 W = a.W, Q = a.Q, RT = ctx->RT;
+    const size_t at = ctx->tick_narrow ? 4 : 8;
+    const u32 n_pos = a.L * Q;
+    size_t o = 0;
+    auto put = [&](size_t bytes) { const size_t at_ = o; o = (o + bytes + 15) & ~size_t(15); return (u32)at_; };
+    a.sm.fr = put((size_t)W * RT * at);
+    a.sm.unt = put((size_t)W * 4);
+    a.sm.remtime = put((size_t)W * 8);
+    a.sm.excl = put(W);
+    a.sm.td = put((size_t)W * 2);
+    a.sm.frontier = put((size_t)Q * 2);
+    a.sm.glist = put((size_t)n_pos * 8);
+    a.sm.gcl = put((size_t)n_pos * 4);
+    auto opt = [&](size_t bytes, bool wanted) -> u32 {
+        if (!wanted || o + bytes + 16 > budget) return SM_NONE;
+        return put(bytes);
+    };
+    a.sm.classes = opt(a.classes_bytes, true);
+    a.sm.vorder = opt((size_t)Q * HQS_MAX_VARIANTS, true);
+    a.sm.rem = opt((size_t)W * RT * 8, ctx->tick_narrow);
+    a.sm.blocked = opt((size_t)W * Q, a.blocked != nullptr);
+    a.sm.bef = opt((size_t)n_pos * 4, sharded);
+    a.sm.loc = a.sm.bef != SM_NONE ? opt((size_t)n_pos * 4, sharded) : SM_NONE;
+    if (a.sm.loc == SM_NONE) a.sm.bef = SM_NONE;
+    a.smem_solver = (u32)o;
+    return o;
+}
+
+// Launches the tick kernel.  counts: nullptr (count inside the kernel), or host-provided totals (NCCL variant, the
+// histogram was taken by hqs_shard_count).  emit = false: what-if query (nothing is emitted or consumed).
+int launch_tick(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, bool blocked, const u32* d_counts_all,
+                const u32* d_before, u32 out_cap, bool emit, bool exchange) {
+    TickArgs a = base_args(ctx, t, W, lay, blocked);
+    a.out_cap = out_cap;
+    a.flags = (d_counts_all ? 0u : TF_COUNT) | (emit ? TF_EMIT : 0u) | (ctx->pack ? TF_PACK : 0u);
+    a.total_ext = d_counts_all;
+    a.before_ext = d_before;
+    if (exchange) {
+        for (u32 r = 0; r < HQS_MAX_PEERS; ++r) a.x_peer[r] = r < ctx->x_world ? ctx->x_peer[r] : nullptr;
+        a.x_world = ctx->x_world; a.x_rank = ctx->x_rank; a.x_seq = ctx->x_seq;
+        a.x_all = ctx->d_xall; a.x_before = ctx->d_xbefore;
+    }
+    const void* fn = tick_fn(ctx->RT, ctx->tick_narrow);
+    const size_t budget = ctx->smem_budget[ctx->tick_narrow ? 0 : 1];
+    const size_t solver_smem = solver_layout(ctx, a, budget, exchange || d_before != nullptr);
+    const size_t smem = std::max(solver_smem, t.worker_smem);
+    if (smem > budget) return fail(ctx, HQS_E_LIMIT, "tick needs %zu bytes of shared memory, %zu available", smem, budget);
+    if (ctx->sync_dirty) {
+        CU(cudaMemsetAsync(ctx->d_sync, 0, sizeof(TickSync), ctx->stream));
+        ctx->sync_dirty = false;
+    }
+    ctx->ev_valid = false;
+    if (ctx->profile) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     void* kargs[] = {&a};
-    const bool small = a.smem_classes != 0;
-    const void* fn;
-#define HQS_PICK(MT, SM, AT) (ctx->RT == 4 ? (const void*)solve_k<4, MT, SM, AT> : ctx->RT == 8 ? (const void*)solve_k<8, MT, SM, AT> : (const void*)solve_k<16, MT, SM, AT>)
-#define HQS_PICK2(MT, SM) (narrow ? HQS_PICK(MT, SM, u32) : HQS_PICK(MT, SM, u64))
-    if (threads <= 256) fn = small ? HQS_PICK2(256, true) : HQS_PICK2(256, false);
-    else fn = small ? HQS_PICK2(1024, true) : HQS_PICK2(1024, false);
-#undef HQS_PICK2
-#undef HQS_PICK
-    static const bool no_coop = getenv("HQS_DEBUG_NO_COOP") != nullptr;   // profiling aid: ncu skips cooperative launches
-    if (no_coop) CU(cudaLaunchKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
-    else CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, solve_smem, ctx->stream));
-    ctx->stats.kernel_launches++;
-    if (ctx->profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (!no_emit)
-    emit_k<<<t.P, 32 * t.emit_warps, t.emit_smem, ctx->stream>>>(
-        ctx->d_key, ctx->n_handles, t.chunk, ctx->Q, t.G, t.g_smem, t.nbits, ctx->d_table, d_before, ctx->d_gout, ctx->d_seg_cum,
-        ctx->d_seg_wv, ctx->d_hdr, ctx->d_out, out_cap);
+    static const bool no_coop = getenv("HQS_DEBUG_NO_COOP") != nullptr;   // profiling aid: some ncu versions skip cooperative launches
+    if (no_coop) CU(cudaLaunchKernel(fn, dim3(ctx->grid_ctas), dim3(TICK_THREADS), kargs, smem, ctx->stream));
+    else CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->grid_ctas), dim3(TICK_THREADS), kargs, smem, ctx->stream));
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
     if (ctx->profile) { CU(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid = true; }
     ctx->last_W = W; ctx->last_G = t.G; ctx->last_L = t.L;
-    ctx->tick_pending = true;
-    ctx->stats.ticks++;
+    return HQS_OK;
+}
+
+// waits for the tick kernel and reads the header the kernel wrote into the pinned mirror
+int wait_header(hqs_ctx* ctx, TickHeaderOut* hdr) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(hdr, ctx->h_hdr, sizeof *hdr);
+    ctx->stats.n_groups = hdr->n_groups;
+    ctx->stats.n_levels = ctx->last_L;
+    ctx->stats.n_assigned = hdr->n_assigned;
+    ctx->stats.n_segments = hdr->n_segments;
+    memcpy(ctx->dbg, hdr->dbg, sizeof ctx->dbg);
+    if (ctx->profile && ctx->ev_valid) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess && hdr->dbg[5]) {
+            const double cyc = (double)hdr->dbg[5];
+            ctx->last_ms[0] = (float)(ms * (double)hdr->dbg[0] / cyc);
+            ctx->last_ms[1] = (float)(ms * (double)(hdr->dbg[1] + hdr->dbg[2]) / cyc);
+            ctx->last_ms[2] = (float)(ms * (double)hdr->dbg[3] / cyc);
+            ctx->last_ms[3] = ms;
+        }
+    }
+    if (hdr->error) ctx->sync_dirty = true;
+    if (hdr->error == 2) return fail(ctx, HQS_E_CUDA, "a grid synchronisation of the tick kernel timed out");
+    if (hdr->error == 1) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
     return HQS_OK;
 }
 
@@ -599,21 +680,16 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newcnt, sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     {
-        const void* fns[] = {
-#define HQS_ALL(RTV, AT) (const void*)solve_k<RTV, 256, true, AT>, (const void*)solve_k<RTV, 256, false, AT>, \
-                         (const void*)solve_k<RTV, 1024, true, AT>, (const void*)solve_k<RTV, 1024, false, AT>
-            HQS_ALL(4, u64), HQS_ALL(8, u64), HQS_ALL(16, u64), HQS_ALL(4, u32), HQS_ALL(8, u32), HQS_ALL(16, u32)
-#undef HQS_ALL
-        };
+        const void* fns[] = {(const void*)tick_k<4, u32>, (const void*)tick_k<8, u32>, (const void*)tick_k<16, u32>,
+                             (const void*)tick_k<4, u64>, (const void*)tick_k<8, u64>, (const void*)tick_k<16, u64>};
         // dynamic + static shared memory of a CTA may not exceed 227 KB: allow each instance what its statics leave
         for (const void* f : fns) {
             cudaFuncAttributes fa;
             if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, f);
             if (e == cudaSuccess) {
                 const size_t room = 227 * 1024 - fa.sharedSizeBytes;
-                e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(room, 200 * 1024));
+                e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(room, 216 * 1024));
             }
         }
     }
@@ -623,6 +699,19 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
         return HQS_E_CUDA;
     }
     ctx->sm_count = sms > 0 ? (u32)sms : 148;
+    // one CTA per SM (cooperative launch: all CTAs are co-resident).  HQS_CREATE_SHARE_DEVICE: half of the SMs, so
+    // that two contexts whose ticks wait for each other on the device (peer exchange) can run side by side on one GPU
+    ctx->grid_ctas = std::max<u32>(2, (flags & 4u) ? ctx->sm_count / 2 : ctx->sm_count);
+    {
+        static const bool copy_in = getenv("HQS_DEBUG_COPY_INPUT") != nullptr;   // debugging aid: H2D copy instead of reading pinned memory in place
+        int can_map = 0;
+        cudaDeviceGetAttribute(&can_map, cudaDevAttrCanMapHostMemory, device);
+        ctx->zero_copy = can_map != 0 && !copy_in;
+    }
+    for (int nw = 0; nw < 2; ++nw) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, tick_fn(ctx->RT, nw == 0)) == cudaSuccess) ctx->smem_budget[nw] = (size_t)fa.maxDynamicSharedSizeBytes;
+    }
     *out = ctx;
     return HQS_OK;
 }
@@ -633,7 +722,7 @@ void hqs_destroy(hqs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* dev_ptrs[] = {ctx->d_classes, ctx->d_classes32, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
                         ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
-                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_glist, ctx->d_seg_cum,
+                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_rem_scratch, ctx->d_excl, ctx->d_seg_cum,
                         ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
                         ctx->d_pk_quota, ctx->d_pk_taken, ctx->d_pk_cand, ctx->d_pk_meta};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
@@ -941,22 +1030,18 @@ int hqs_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
     if (!ctx) return HQS_E_INVALID;
     int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
     if (rc) return rc;
+    if (ctx->tick_pending) return fail(ctx, HQS_E_STATE, "the previous tick has not been fetched");
     CU(cudaSetDevice(ctx->device));
     const TickGeom t = tick_geom(ctx);
     if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
     if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap))) return rc;
     TickLayout lay;
-    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
-    if (ctx->n_handles == 0) {
-        // nothing was ever pushed: an empty tick still has to produce a header
-        CU(cudaMemsetAsync(ctx->d_hdr, 0, sizeof(TickHeaderOut), ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_free_after, ctx->d_tickin + lay.off_free, (size_t)n_workers * ctx->R * 8,
-                           cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->last_W = n_workers; ctx->tick_pending = true; ctx->stats.ticks++;
-        return HQS_OK;
-    }
-    if ((rc = launch_count(ctx, t))) return rc;
-    return launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, out_cap);
+    bool has_mu, any_time;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay, &has_mu, &any_time))) return rc;
+    if ((rc = launch_tick(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, out_cap, true, false))) return rc;
+    ctx->tick_pending = true;
+    ctx->stats.ticks++;
+    return HQS_OK;
 }
 
 int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t* out_n, uint64_t* free_after) {
@@ -964,30 +1049,14 @@ int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t
     if (!ctx->tick_pending) return fail(ctx, HQS_E_STATE, "no tick in flight");
     if (out_n) *out_n = 0;
     CU(cudaSetDevice(ctx->device));
-    const size_t fa_bytes = (size_t)ctx->last_W * ctx->R * 8;
-    const size_t need = sizeof(TickHeaderOut) + fa_bytes;
-    if (need > ctx->h_hdr_cap) {
-        if (ctx->h_hdr) CU(cudaFreeHost(ctx->h_hdr));
-        ctx->h_hdr_cap = need * 2;
-        CU(cudaMallocHost(&ctx->h_hdr, ctx->h_hdr_cap));
-    }
-    CU(cudaMemcpyAsync(ctx->h_hdr, ctx->d_hdr, sizeof(TickHeaderOut), cudaMemcpyDeviceToHost, ctx->stream));
-    if (free_after)
-        CU(cudaMemcpyAsync(ctx->h_hdr + sizeof(TickHeaderOut), ctx->d_free_after, fa_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     ctx->tick_pending = false;
     TickHeaderOut hdr;
-    memcpy(&hdr, ctx->h_hdr, sizeof hdr);
-    ctx->stats.n_groups = hdr.n_groups;
-    ctx->stats.n_levels = ctx->last_L;
-    ctx->stats.n_assigned = hdr.n_assigned;
-    ctx->stats.n_segments = hdr.n_segments;
-    memcpy(ctx->dbg, hdr.dbg, sizeof ctx->dbg);
-    if (hdr.error == 2) return fail(ctx, HQS_E_CUDA, "solver grid synchronisation timed out");
-    if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
-    if (hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
+    int rc = wait_header(ctx, &hdr);
+    if (rc) return rc;
+    // error 3: the solver saw that out_cap is too small BEFORE the emit step: nothing was emitted, the ready set is intact
+    if (hdr.error == 3 || hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
         return fail(ctx, HQS_E_OVERFLOW, "out_cap=%u too small for %u assignments", out_cap, hdr.n_assigned);
-    if (free_after) memcpy(free_after, ctx->h_hdr + sizeof(TickHeaderOut), fa_bytes);
+    if (free_after) memcpy(free_after, ctx->h_hdr + sizeof(TickHeaderOut), (size_t)ctx->last_W * ctx->R * 8);
     if (hdr.n_assigned) {
         CU(cudaMemcpyAsync(out, ctx->d_out, (size_t)hdr.n_assigned * sizeof(hqs_assignment), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1011,34 +1080,26 @@ int hqs_query(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers, const
     if (n_would_assign) *n_would_assign = 0;
     int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
     if (rc) return rc;
+    if (ctx->tick_pending) return fail(ctx, HQS_E_STATE, "the previous tick has not been fetched");
     CU(cudaSetDevice(ctx->device));
     const TickGeom t = tick_geom(ctx);
     if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
     if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, 1024))) return rc;
     TickLayout lay;
-    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
-    if (ctx->n_handles == 0) {
-        if (per_worker_assigned) memset(per_worker_assigned, 0, n_workers * sizeof(u32));
-        if (free_after) memcpy(free_after, free_rw, (size_t)n_workers * ctx->R * 8);
-        return HQS_OK;
-    }
-    if ((rc = launch_count(ctx, t))) return rc;
-    if ((rc = launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, 0, true))) return rc;
-    ctx->tick_pending = false;      // nothing was emitted or consumed
-    ctx->stats.ticks--;
+    bool has_mu, any_time;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay, &has_mu, &any_time))) return rc;
+    // same kernel, no emit step: nothing is emitted or consumed
+    if ((rc = launch_tick(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, 0, false, false))) return rc;
     u32* d_pw = ctx->d_pk_quota;    // scratch (pack is over): [W] counters
     CU(cudaMemsetAsync(d_pw, 0, n_workers * sizeof(u32), ctx->stream));
-    seg_worker_totals_k<<<(t.G + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_hdr, ctx->d_gout, t.G, ctx->d_seg_cum, ctx->d_seg_wv, d_pw);
+    seg_worker_totals_k<<<(t.G + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_gout, t.G, ctx->d_seg_cum, ctx->d_seg_wv, d_pw);
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
-    TickHeaderOut hdr;
     std::vector<u32> pw(n_workers);
-    CU(cudaMemcpyAsync(&hdr, ctx->d_hdr, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(pw.data(), d_pw, n_workers * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    if (free_after) CU(cudaMemcpyAsync(free_after, ctx->d_free_after, (size_t)n_workers * ctx->R * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (hdr.error == 2) return fail(ctx, HQS_E_CUDA, "solver grid synchronisation timed out");
-    if (hdr.error) return fail(ctx, HQS_E_LIMIT, "count-segment overflow");
+    TickHeaderOut hdr;
+    if ((rc = wait_header(ctx, &hdr))) return rc;
+    if (free_after) memcpy(free_after, ctx->h_hdr + sizeof(TickHeaderOut), (size_t)n_workers * ctx->R * 8);
     if (n_would_assign) *n_would_assign = hdr.n_assigned;
     if (per_worker_assigned) memcpy(per_worker_assigned, pw.data(), n_workers * sizeof(u32));
     return HQS_OK;
@@ -1051,21 +1112,27 @@ int hqs_shard_count(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* workers,
     int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
     if (rc) return rc;
     if (!d_counts) return fail(ctx, HQS_E_INVALID, "null d_counts");
+    if (ctx->tick_pending) return fail(ctx, HQS_E_STATE, "the previous tick has not been fetched");
     CU(cudaSetDevice(ctx->device));
     const TickGeom t = tick_geom(ctx);
     if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
     if (t.G > n_groups_cap) return fail(ctx, HQS_E_LIMIT, "groups=%u > n_groups_cap=%u", t.G, n_groups_cap);
     if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, 1024))) return rc;
     TickLayout lay;
-    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
+    bool has_mu, any_time;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay, &has_mu, &any_time))) return rc;
+    CU(cudaMemsetAsync(ctx->d_total, 0, (size_t)t.G * 4, ctx->stream));
     if (ctx->n_handles) {
-        if ((rc = launch_count(ctx, t))) return rc;
+        TickArgs a = base_args(ctx, t, n_workers, lay, blocked_wcv != nullptr);
+        count_only_k<<<std::min<u32>(t.P, ctx->sm_count * 2), TICK_THREADS, t.G * sizeof(u32), ctx->stream>>>(a);
+        ctx->stats.kernel_launches++;
+        CU(cudaGetLastError());
     }
     CU(cudaMemsetAsync(d_counts, 0, (size_t)n_groups_cap * 4, ctx->stream));
     CU(cudaMemcpyAsync(d_counts, ctx->d_total, (size_t)t.G * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->last_W = n_workers;
-    ctx->h_small[8] = blocked_wcv ? 1u : 0u;
+    ctx->last_blocked = blocked_wcv != nullptr;
     if (n_groups) *n_groups = t.G;
     return HQS_OK;
 }
@@ -1078,8 +1145,11 @@ int hqs_shard_solve_emit(hqs_ctx* ctx, const uint32_t* d_counts_all, const uint3
     const TickGeom t = tick_geom(ctx);
     int rc = ensure_tick_buffers(ctx, t.G, t.P, ctx->last_W, out_cap);
     if (rc) return rc;
-    const TickLayout lay = tick_layout(ctx->last_W, ctx->R, ctx->Q, ctx->h_small[8] != 0);
-    return launch_solve_emit(ctx, t, ctx->last_W, lay, ctx->h_small[8] != 0, d_counts_all, d_ranks_before, out_cap);
+    const TickLayout lay = tick_layout(ctx->last_W, ctx->R, ctx->Q, ctx->last_blocked);
+    if ((rc = launch_tick(ctx, t, ctx->last_W, lay, ctx->last_blocked, d_counts_all, d_ranks_before, out_cap, true, false))) return rc;
+    ctx->tick_pending = true;
+    ctx->stats.ticks++;
+    return HQS_OK;
 }
 
 int hqs_tick_reserve(hqs_ctx* ctx, uint32_t n_workers, uint32_t out_cap, int with_blocked) {
@@ -1092,18 +1162,7 @@ int hqs_tick_reserve(hqs_ctx* ctx, uint32_t n_workers, uint32_t out_cap, int wit
     int rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap);
     if (rc) return rc;
     const TickLayout lay = tick_layout(n_workers, ctx->R, ctx->Q, with_blocked != 0);
-    if (lay.bytes > ctx->tickin_cap) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_tickin) CU(cudaFree(ctx->d_tickin));
-        if (ctx->h_tickin) CU(cudaFreeHost(ctx->h_tickin));
-        ctx->tickin_cap = lay.bytes * 2;
-        CU(cudaMalloc(&ctx->d_tickin, ctx->tickin_cap));
-        CU(cudaMallocHost(&ctx->h_tickin, ctx->tickin_cap));
-    }
-    if (!ctx->h_hdr) {
-        ctx->h_hdr_cap = sizeof(TickHeaderOut) + (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * 8;
-        CU(cudaMallocHost(&ctx->h_hdr, ctx->h_hdr_cap));
-    }
+    if ((rc = ensure_tickin(ctx, lay.bytes))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     return HQS_OK;
 }
@@ -1169,29 +1228,20 @@ int hqs_shard_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* wo
     if (!ctx->x_world) return fail(ctx, HQS_E_STATE, "hqs_shard_attach has not been called");
     int rc = validate_workers(ctx, n_workers, workers, free_rw, total_rw);
     if (rc) return rc;
+    if (ctx->tick_pending) return fail(ctx, HQS_E_STATE, "the previous tick has not been fetched");
     CU(cudaSetDevice(ctx->device));
     const TickGeom t = tick_geom(ctx);
     if (t.G > HQS_MAX_GROUPS) return fail(ctx, HQS_E_LIMIT, "groups=%u > %u", t.G, HQS_MAX_GROUPS);
     if ((rc = ensure_tick_buffers(ctx, t.G, t.P, n_workers, out_cap))) return rc;
     TickLayout lay;
-    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay))) return rc;
-    if (ctx->n_handles) {
-        if ((rc = launch_count(ctx, t))) return rc;
-    } else {
-        CU(cudaMemsetAsync(ctx->d_total, 0, (size_t)t.G * 4, ctx->stream));
-    }
+    bool has_mu, any_time;
+    if ((rc = upload_tick_input(ctx, n_workers, workers, free_rw, total_rw, blocked_wcv, &lay, &has_mu, &any_time))) return rc;
     // every rank advances the sequence number in lockstep (one sharded tick = one exchange)
     ctx->x_seq += 1;
-    XchgArgs x;
-    for (u32 r = 0; r < HQS_MAX_PEERS; ++r) x.peer[r] = r < ctx->x_world ? ctx->x_peer[r] : nullptr;
-    x.world = ctx->x_world; x.rank = ctx->x_rank; x.seq = ctx->x_seq; x.G = t.G;
-    xchg_k<<<ctx->x_world, 256, 0, ctx->stream>>>(ctx->d_total, x);
-    ctx->stats.kernel_launches++;
-    CU(cudaGetLastError());
-    ctx->x_tick = true;
-    rc = launch_solve_emit(ctx, t, n_workers, lay, blocked_wcv != nullptr, ctx->d_xall, ctx->d_xbefore, out_cap);
-    ctx->x_tick = false;
-    return rc;
+    if ((rc = launch_tick(ctx, t, n_workers, lay, blocked_wcv != nullptr, nullptr, nullptr, out_cap, true, true))) return rc;
+    ctx->tick_pending = true;
+    ctx->stats.ticks++;
+    return HQS_OK;
 }
 
 int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n) {
@@ -1226,13 +1276,7 @@ int hqs_set_profile(hqs_ctx* ctx, int on) {
 int hqs_get_kernel_ms(hqs_ctx* ctx, float out_ms[4]) {
     if (!ctx || !out_ms) return HQS_E_INVALID;
     if (!ctx->profile || !ctx->ev_valid) return fail(ctx, HQS_E_STATE, "no profiled tick available");
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaEventSynchronize(ctx->ev[3]));
-    out_ms[3] = 0;
-    for (int i = 0; i < 3; ++i) {
-        CU(cudaEventElapsedTime(&out_ms[i], ctx->ev[i], ctx->ev[i + 1]));
-        out_ms[3] += out_ms[i];
-    }
+    for (int i = 0; i < 4; ++i) out_ms[i] = ctx->last_ms[i];
     return HQS_OK;
 }
 

@@ -203,38 +203,19 @@ WorkerTaskMapping GpuCore::run_scheduling(uint64_t now_ms) {
         log_error("tick failed, nothing scheduled", last_error_.c_str());
         return mapping;
     }
-    // min_utilization (solver.rs:154-156, 479-518): a worker takes at least min_cpus of new work or nothing
-    std::vector<char> dropped(W, 0);
-    bool any_drop = false;
-    for (uint32_t w = 0; w < W; ++w) {
-        const float mu = hw[w].min_utilization;
-        const uint64_t tot = total_rw[(size_t)w * R_], fr = free_rw[(size_t)w * R_], fa = free_after[(size_t)w * R_];
-        if (mu <= 0.001f || tot == HQS_AMOUNT_MAX) continue;
-        const double min_cpus = (double)tot / 1e4 * ((double)mu - 1.0) + (double)fr / 1e4;
-        const double new_cpus = ((double)fr - (double)fa) / 1e4;
-        if (min_cpus >= 0.0001 && new_cpus > 0 && new_cpus < min_cpus - 1e-9) { dropped[w] = 1; any_drop = true; }
-    }
-    std::vector<uint32_t> back_h, back_c;
-    std::vector<uint64_t> back_p;
+    // min_utilization (solver.rs:154-156, 479-518) is enforced inside the tick: a worker that would receive less than its
+    // minimum is taken out of the solve, which then starts over, so nothing has to be handed back here
     for (uint32_t k = 0; k < n; ++k) {
         const hqs_assignment& a = out_[k];
         TaskState& t = tasks_[a.task];
-        if (any_drop && dropped[a.worker]) {               // the task returns to the ready set
-            back_h.push_back(a.task); back_c.push_back(t.rq); back_p.push_back(t.priority);
-            continue;
-        }
         t.worker = ids[a.worker];
         t.variant = a.variant;
         mapping.workers[ids[a.worker]].assigned.emplace_back(t.id, a.variant);     // emission order = priority desc
     }
     i = 0;
     for (auto& kv : workers_) {
-        if (!dropped[i]) std::copy(free_after.begin() + (size_t)i * R_, free_after.begin() + (size_t)(i + 1) * R_, kv.second.free.begin());
+        std::copy(free_after.begin() + (size_t)i * R_, free_after.begin() + (size_t)(i + 1) * R_, kv.second.free.begin());
         ++i;
-    }
-    if (!back_h.empty() && hqs_ready_push(ctx_, (uint32_t)back_h.size(), back_h.data(), back_c.data(), back_p.data()) != HQS_OK) {
-        last_error_ = hqs_last_error(ctx_);
-        log_error("hqs_ready_push (min_utilization hand-back)", last_error_.c_str());
     }
     return mapping;
 }

@@ -280,36 +280,13 @@ class GpuScheduler:
                                        L.ptr(blocked) if blocked is not None else None, out_cap,
                                        L.ptr(self._out), C.byref(n), L.ptr(free_after)))
         a = self._out[: n.value].copy()
-        a, free_after = self._enforce_min_utilization(a, free, total, free_after)
+        # WorkerConfiguration::min_utilization (solver.rs:154-156, 479-518) is enforced inside the tick kernel: a worker
+        # that would receive less than its minimum is taken out of the solve, which then starts over
         self.free = free_after
         if a.size:
             self._task_worker[a["task"]] = a["worker"]
             self._task_variant[a["task"]] = a["variant"]
         return WorkerTaskMapping(a, self.worker_ids.copy(), free_after)
-
-    def _enforce_min_utilization(self, a: np.ndarray, free: np.ndarray, total: np.ndarray, free_after: np.ndarray):
-        """WorkerConfiguration::min_utilization (solver.rs:154-156, 479-518): a worker either receives at least
-        min_cpus = total * (mu - 1) + free cpus of new work in this tick, or nothing.  The MILP has a boolean per
-        worker for that; the greedy analogue is a post-filter in the shim: the placements of a violating worker
-        are dropped, its free vector is restored and the tasks go back to the ready set."""
-        mu = self.min_utilization.astype(np.float64)
-        if not (mu > 0.001).any() or a.size == 0:
-            return a, free_after
-        cpu_total, cpu_free = total[:, 0].astype(np.float64) / 1e4, free[:, 0].astype(np.float64) / 1e4
-        min_cpus = cpu_total * (mu - 1.0) + cpu_free
-        new_cpus = (free[:, 0].astype(np.float64) - free_after[:, 0].astype(np.float64)) / 1e4
-        known = total[:, 0] != np.uint64(L.HQS_AMOUNT_MAX)
-        bad = (mu > 0.001) & known & (min_cpus >= 0.0001) & (new_cpus > 0) & (new_cpus < min_cpus - 1e-9)
-        if not bad.any():
-            return a, free_after
-        drop = bad[a["worker"]]
-        back = a["task"][drop]
-        free_after = free_after.copy()
-        free_after[bad] = free[bad]
-        self._check(self._lib.hqs_ready_push(self._ctx, back.size, L.ptr(np.ascontiguousarray(back)),
-                                             L.ptr(np.ascontiguousarray(self._task_class[back])),
-                                             L.ptr(np.ascontiguousarray(self._task_prio[back]))))
-        return a[~drop], free_after
 
     def tasks_finished(self, handles, propagate: bool = False) -> int:
         """task_finished for a batch: returns the resources of each task to its worker

@@ -13,7 +13,9 @@
  *  - plain C, no exceptions / longjmp across the ABI, caller-owned host buffers (pinned or pageable),
  *  - every function returns 0 on success and a negative HQS_E_* code on failure; after a failed
  *    hqs_tick the host must schedule NOTHING this tick (mirrors "solver returned None => empty
- *    solution", solver.rs:412-415); hqs_last_error() gives the text,
+ *    solution", solver.rs:412-415) and the device has consumed nothing either: the ready set is as it was
+ *    before the call (HQS_E_OVERFLOW, HQS_E_LIMIT: the solver decides before anything is emitted);
+ *    hqs_last_error() gives the text,
  *  - called from tako's single reactor thread; a context is not thread-safe,
  *  - tasks are named by dense u32 handles chosen by the shim IN TaskId ORDER (ascending handle ==
  *    ascending (job_id, job_task_id)), because the ready set is popped in ascending TaskId inside one
@@ -79,7 +81,8 @@ typedef struct {
     uint32_t worker_id;
     uint32_t flags;              /* reserved, 0                                                   */
     uint64_t remaining_time_ms;  /* termination_time - now, HQS_TIME_INF if none (worker.rs:320)   */
-    float min_utilization;       /* WorkerConfiguration::min_utilization (solver.rs:154-156)       */
+    float min_utilization;       /* WorkerConfiguration::min_utilization (solver.rs:154-156, 479-518): enforced by
+                                    the tick — the worker gets at least total*(mu-1)+free cpus of new work or nothing */
     uint32_t reserved;
 } hqs_worker;
 
@@ -113,6 +116,9 @@ int hqs_abi_version(void);
  *                below 2^31 — same results, shorter critical path).  Both bits exist for tests. */
 #define HQS_CREATE_NO_PACK 1u
 #define HQS_CREATE_WIDE_AMOUNTS 2u
+/*        bit 2 = the tick kernel occupies half of the SMs only, so that two contexts whose ticks wait for each other on
+ *                the device (peer exchange between two contexts of one GPU) can run side by side. */
+#define HQS_CREATE_SHARE_DEVICE 4u
 int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags);
 void hqs_destroy(hqs_ctx* ctx);
 const char* hqs_last_error(const hqs_ctx* ctx);   /* ctx may be NULL: last error of hqs_create */
@@ -214,12 +220,14 @@ void* hqs_stream(hqs_ctx* ctx);                 /* cudaStream_t of the context  
 /* Makes the context enqueue its work on an externally owned stream (e.g. the host framework's current
  * stream) so that several contexts serialise on one stream and foreign events can time them. */
 int hqs_set_stream(hqs_ctx* ctx, void* cuda_stream);
-/* Per-kernel device timing of the tick (CUDA events on the context stream, off by default).
- * out_ms[0..2] = count_k, solve_k, emit_k of the last fetched/synchronised tick, out_ms[3] = their sum. */
+/* Device timing of the tick (off by default).  out_ms[3] = the tick kernel between two CUDA events on the context
+ * stream; out_ms[0..2] = its phases as seen by the solver CTA's clock (staging + wait for the histogram, exchange +
+ * compaction + solve, emit), scaled to out_ms[3].  Valid after the tick has been fetched. */
 int hqs_set_profile(hqs_ctx* ctx, int on);
 int hqs_get_kernel_ms(hqs_ctx* ctx, float out_ms[4]);
-/* Debug: clock64 phase stamps of the solver CTA of the last fetched tick (compaction, saturation tests,
- * group loop, total, non-empty groups). */
+/* Debug: phase lengths of the solver CTA of the last fetched tick in SM clock cycles: [0] staging + wait for the
+ * histogram, [1] exchange + compaction + demand, [2] the solver warp, [3] emit, [4] non-empty groups, [5] whole
+ * kernel, [6] whole kernel in nanoseconds (globaltimer), [7] pack commands. */
 int hqs_debug_read(hqs_ctx* ctx, uint64_t out[8]);
 int hqs_sync(hqs_ctx* ctx);
 int hqs_get_stats(hqs_ctx* ctx, hqs_stats* out);

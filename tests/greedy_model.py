@@ -18,7 +18,7 @@ The algorithm, per tick:
   before and after, and whatever the packed level could not place — is priority-ordered first-fit over
   workers in ascending id (compaction, solver.rs (n - w_idx)/n); a worker tries the variants of a class in
   ascending order of the same "share of what I have left" cost, re-evaluated after each variant.
-Mirrors class_order(), solve_body() / pack_body(), emit_k().
+Mirrors tick_orders() (hqsched.cu), solver_cta() / emit_chunk() (hqs_tick.cuh) and pack_body() (hqs_solver.cuh).
 """
 from __future__ import annotations
 
@@ -110,8 +110,11 @@ class _Tick:
         self.am = [[{r: int(a) for r, a in d["amounts"].items()} for d in vs] for vs in wl.classes]
         self.alls = [[tuple(d.get("all", ())) for d in vs] for vs in wl.classes]
         self.min_ms = [[int(round(d.get("min_time_s", 0.0) * 1000)) for d in vs] for vs in wl.classes]
+        self.excluded = None
 
     def admissible(self, w: int, c: int, v: int) -> bool:
+        if self.excluded is not None and self.excluded[w]:
+            return False
         if self.wl.blocked is not None and self.wl.blocked[w, c, v]:
             return False
         rt = self.rem_ms[w]
@@ -183,6 +186,8 @@ def _level_is_saturated(t: _Tick, groups: List[Tuple[int, int]], vorder: List[Li
     for r in range(R):
         s = 0
         for w in range(W):
+            if t.excluded is not None and t.excluded[w]:
+                continue
             s = U64 if t.fr[w][r] == AMOUNT_MAX else _sat_add(s, t.fr[w][r])
             if s == U64:
                 break
@@ -281,8 +286,40 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tup
 
 
 def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Optional[np.ndarray] = None,
-               remaining_ms: Optional[np.ndarray] = None, pack: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """Returns (assignments in device emission order, free_after)."""
+               remaining_ms: Optional[np.ndarray] = None, pack: bool = True,
+               min_utilization: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Returns (assignments in device emission order, free_after).
+
+    min_utilization (solver.rs:154-156, 479-518): a worker either receives at least
+    min_cpus = total * (mu - 1) + free cpus of new work in this tick, or nothing.  A violating worker is taken out of
+    the tick and the solve starts over (at most MU_MAX_PASSES - 1 times), so its tasks go to the other workers."""
+    W = free.shape[0]
+    excluded = np.zeros(W, dtype=bool)
+    for p in range(MU_MAX_PASSES):
+        a, fa = _solve_pass(wl, ready, free, levels, remaining_ms, pack, excluded)
+        if min_utilization is None or p + 1 >= MU_MAX_PASSES:
+            return a, fa
+        viol = False
+        for w in range(W):
+            mu = float(np.float32(min_utilization[w]))
+            t0, f0 = int(wl.worker_total[w, 0]), int(free[w, 0])
+            if excluded[w] or not (np.float32(min_utilization[w]) > np.float32(0.001)) or t0 == AMOUNT_MAX or f0 == AMOUNT_MAX:
+                continue
+            min_cpus = (float(t0) / 10000.0) * (mu - 1.0) + float(f0) / 10000.0
+            new_cpus = float(f0 - int(fa[w, 0])) / 10000.0
+            if min_cpus >= 0.0001 and new_cpus > 0.0 and new_cpus < min_cpus - 1e-9:
+                excluded[w] = True
+                viol = True
+        if not viol:
+            return a, fa
+    raise AssertionError("unreachable")
+
+
+MU_MAX_PASSES = 8
+
+
+def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remaining_ms, pack: bool,
+                excluded: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     W, R = free.shape
     prio = wl.task_user_priority.astype(np.int64)
     if levels is None:
@@ -290,6 +327,7 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
     if remaining_ms is None:
         remaining_ms = wl.remaining_ms()
     t = _Tick(wl, free, remaining_ms)
+    t.excluded = [bool(x) for x in excluded]
     order = class_order(wl, free, wl.worker_total)
     vorder = variant_order(wl, free)
     out: List[Tuple[int, int, int, int]] = []
@@ -307,7 +345,7 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
         if not packed:
             n_cand = sum(len(t.am[c]) for c, _ in groups)
             has_all = any(t.alls[c][v] for c, _ in groups for v in range(len(t.am[c])))
-            if n_cand <= PACK_MAX_CAND and not has_all:
+            if n_cand <= PACK_MAX_CAND and len(groups) <= PACK_MAX_CAND and not has_all:
                 saturated, phi = _level_is_saturated(t, groups, vorder)
                 if saturated:
                     taken = _pack_level(t, groups, phi)

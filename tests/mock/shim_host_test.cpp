@@ -1,6 +1,6 @@
 // Host-logic checks of tako_b200::GpuCore against the test double of the C ABI (fake_hqsched.cpp): what the shim
 // does around a tick — interning, handle mapping, batched pushes, applying the result to its worker mirror,
-// min_utilization hand-back, resource return, worker removal.  Returns the number of failed checks.
+// resource return, worker removal (min_utilization is enforced inside the library's tick: tests/test_gpu_edges.py).  Returns the number of failed checks.
 #include "../../include/tako_shim.hpp"
 
 #include <cstdio>
@@ -66,21 +66,6 @@ int main() {
         core.on_remove_worker(1);                                      // task {2,2} was running there
         m = core.run_scheduling();
         check(m.n_assigned() == 1 && m.workers.count(2) && m.workers[2].assigned[0].first == (TaskId{2, 2}), "tasks of a lost worker are rescheduled");
-    }
-    {   // min_utilization: 3-cpu tasks on a 12-cpu worker (test_schedule_min_utilization1, test_scheduler_sn.rs:1391-1414)
-        const struct { int n; float mu; size_t expect; } rows[] = {{2, 0.5f, 2}, {2, 0.51f, 0}, {3, 0.51f, 3}, {3, 0.75f, 3}, {3, 0.76f, 0}};
-        for (const auto& row : rows) {
-            GpuCore core(1, 0);
-            const ResourceRqId c3 = core.get_or_create_resource_rq_id(cpus(3));
-            core.on_new_worker(1, {12 * FRACTIONS_PER_UNIT}, row.mu);
-            for (int t = 0; t < row.n; ++t) core.add_ready_task(TaskId{3, (uint32_t)t}, c3, priority_from_user(0));
-            const WorkerTaskMapping m = core.run_scheduling();
-            check(m.n_assigned() == row.expect, "min_utilization: all or nothing");
-            if (row.expect == 0) {
-                check(core.free_resources(1)[0] == 12 * FRACTIONS_PER_UNIT, "dropped placements leave the worker untouched");
-                check(core.stats().kernel_launches == (uint64_t)2 * row.n, "dropped tasks are pushed back into the ready set");
-            }
-        }
     }
     {   // error behaviour: invalid requests throw, like the reference's panics
         GpuCore core(1, 0);

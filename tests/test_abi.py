@@ -99,13 +99,16 @@ def test_cpp_shim_builds_and_exports_the_reference_interface(lib):
 
 
 def test_solver_shared_memory_budget(lib):
-    """Every solver instance must leave room for its worst-case dynamic shared memory (class table <= 48 KB, 2048
-    buffered groups, 4096 buffered segments: ~140 KB) inside the 227 KB a CTA may use — otherwise context set-up
-    fails on the device, which the CPU-only box would not notice."""
+    """Every instance of the tick kernel must leave room for its worst-case MANDATORY dynamic shared memory (1024 workers
+    x 16 resource slots x 8 B of free amounts + per-worker words + 4096 group-list entries: ~200 KB) inside the 227 KB
+    a CTA may use — otherwise a tick fails on the device, which the CPU-only box would not notice."""
     import subprocess
     from hyperqueue_b200 import _lib
     out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    statics = [int(m) for blk in re.findall(r"Function [^\n]*solve_k[^\n]*\n[^\n]*", out) for m in re.findall(r"SHARED:(\d+)", blk)]
-    assert len(statics) >= 24
-    worst_dynamic = 48 * 1024 + 2048 * (8 + 4 + 1 + 16) + 256 + 2 * 4096 * 4 + 64
-    assert max(statics) + worst_dynamic <= 227 * 1024, (max(statics), worst_dynamic)
+    statics = [int(m) for blk in re.findall(r"Function [^\n]*tick_k[^\n]*\n[^\n]*", out) for m in re.findall(r"SHARED:(\d+)", blk)]
+    assert len(statics) == 6
+    W, Q, n_pos = 1024, 4096, 4096
+    worst_mandatory = W * 16 * 8 + W * (4 + 8 + 1 + 2) + Q * 2 + n_pos * 12 + 8 * 16
+    assert max(statics) + worst_mandatory <= 227 * 1024, (max(statics), worst_mandatory)
+    # the emit step of the worker CTAs: <= 128 KB of counters + 64 KB of group records + the segment cache
+    assert max(statics) + 128 * 1024 + 64 * 1024 + 8 * 1024 <= 227 * 1024

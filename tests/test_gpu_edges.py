@@ -141,7 +141,8 @@ def test_error_contract():
 
 
 def test_min_utilization_vectors():
-    """test_schedule_min_utilization1/2 (test_scheduler_sn.rs:1391-1445) through the shim's post-filter."""
+    """test_schedule_min_utilization1/2 (test_scheduler_sn.rs:1391-1445): the rule is enforced inside the tick kernel (a
+    violating worker is taken out of the solve, which starts over)."""
     from hyperqueue_b200 import GpuScheduler, RequestVariant, priority_from_user
 
     def run(n_tasks, w_cpus, mu, running_cpus=0):
@@ -163,6 +164,54 @@ def test_min_utilization_vectors():
         assert got == exp, (n, mu, got)
         if exp == 0:
             assert again == 0 and int(free[0, 0]) == 12 * FR      # dropped tasks are ready again; nothing leaked
+
+
+def test_min_utilization_moves_work_to_other_workers():
+    """A worker that cannot reach its minimum utilisation gets nothing — and its tasks go to the workers that can take
+    them in the SAME tick (the reference's MILP does this with one boolean per worker, solver.rs:479-518).  Checked
+    against the specification bit for bit, on a single-variant and on a three-variant pool."""
+    from hyperqueue_b200 import GpuScheduler, RequestVariant, priority_from_user
+    # w0 wants to be full (mu = 1.0, 4 cpus), w1 takes anything: one 1-cpu task must land on w1, not starve
+    s = GpuScheduler(1)
+    c = s.get_or_create_resource_rq_id([RequestVariant.of({0: 1 * FR})])
+    s.new_worker(1, [4 * FR], min_utilization=1.0)
+    s.new_worker(2, [4 * FR])
+    s.add_ready_tasks(np.arange(1, dtype=np.uint32), np.full(1, c, dtype=np.uint32), priority_from_user(np.zeros(1)))
+    m = s.run_scheduling()
+    assert m.n_assigned() == 1 and m.per_worker() == {2: [(0, 0)]}
+    assert int(s.free[0, 0]) == 4 * FR and int(s.free[1, 0]) == 3 * FR
+    s.close()
+    for seed, v3 in [(31, False), (32, True)]:
+        wl = P.make_independent(3000, 12, 6, seed=seed, variants3=v3)
+        mu = np.zeros(12, dtype=np.float32)
+        mu[[0, 3, 7]] = [1.0, 0.97, 0.9]
+        sch = P.gpu_scheduler(wl)
+        sch.min_utilization = mu.copy()
+        fb = sch.free.copy()
+        m = sch.run_scheduling()
+        exp, exp_free = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), fb, min_utilization=mu)
+        assert P.judge_tick(wl, fb, m.assignments).ok
+        assert np.array_equal(m.assignments, exp) and np.array_equal(m.free_after, exp_free)
+        # the rule itself: every worker with a minimum got either nothing or at least its minimum
+        new_cpus = (fb[:, 0].astype(np.float64) - m.free_after[:, 0].astype(np.float64)) / 1e4
+        min_cpus = wl.worker_total[:, 0] / 1e4 * (mu.astype(np.float64) - 1.0) + fb[:, 0] / 1e4
+        assert ((new_cpus == 0) | (new_cpus >= min_cpus - 1e-9) | (mu <= 0.001)).all()
+        sch.close()
+
+
+def test_too_small_out_cap_fails_before_anything_is_consumed():
+    """ABI contract: after a failed hqs_tick the host schedules nothing — so the device must not have consumed anything
+    either.  The solver knows the number of assignments before the emit step and skips it."""
+    from hyperqueue_b200 import HqsError
+    wl = P.make_independent(5000, 8, 4, seed=9, free_scale=64)
+    s = P.gpu_scheduler(wl)
+    with pytest.raises(HqsError) as ei:
+        s.run_scheduling(out_cap=100)
+    assert ei.value.code == -5
+    m = s.run_scheduling()                                # the whole ready set is still there
+    exp, _ = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), wl.worker_free)
+    assert np.array_equal(m.assignments, exp) and m.n_assigned() > 100
+    s.close()
 
 
 def test_new_worker_query_is_a_dry_run():

@@ -91,7 +91,8 @@ def test_two_shards_peer_exchange_on_one_gpu(n, w, q, scale):
     xb = (C.c_void_p * 2)()
     for r in range(2):
         lo, hi = block_range(n, r, 2)
-        s = P.gpu_scheduler(_shard_workload(wl, lo, hi), add_tasks=False)
+        # the two ticks wait for each other on the device: each kernel takes half of the SMs
+        s = P.gpu_scheduler(_shard_workload(wl, lo, hi), add_tasks=False, flags=L.HQS_CREATE_SHARE_DEVICE)
         lv = np.ascontiguousarray(np.unique(priority_from_user(wl.task_user_priority)))
         s._sync_classes()
         s._check(s._lib.hqs_levels_add(s._ctx, lv.size, L.ptr(lv)))
