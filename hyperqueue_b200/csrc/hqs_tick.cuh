@@ -611,7 +611,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     //      demand never exceeds (total demand - what earlier levels consumed), so "total demand fits the pool"
     //      rules saturation out for the whole tick and the per-level tests are skipped (mode M1).
     bool skip_sat = (a.flags & TF_PACK) == 0;
-    if (!skip_sat) {
+    {
         u64 val[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) val[r] = 0;
@@ -649,8 +649,11 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         __syncthreads();
         bool fits = s_multi == 0;
         for (u32 r = 0; r < R; ++r) fits &= s_C[r] == HQS_AMOUNT_MAX || s_D[r] <= s_C[r];
-        skip_sat = fits;
+        skip_sat = skip_sat || fits;
     }
+    // plain tick: one variant per class, no `All`, no blocked mask, no time limits, no minimum utilisation.  Its
+    // first-fit runs in the lean loop below (worker tile in registers, next group prefetched).
+    const bool plain = s_multi == 0 && !blocked && !a.any_time_limit && !a.min_util;
     __syncthreads();
     const long long t_prologue = clock64();
 
@@ -789,7 +792,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         atomicAnd(&s_unt[w], ~touched);
                     }
                     if (k) *tk = k - use;
-                    if (__ballot_sync(0xffffffffu, k > use)) { ex_lo = ex_lo < tile ? ex_lo : tile; ex_hi = tile + 1; }
+                    if (__ballot_sync(0xffffffffu, k > use)) { ex_lo = ex_lo < tile ? ex_lo : tile; ex_hi = ex_hi > tile + 1 ? ex_hi : tile + 1; }
                     nseg += __popc(um);
                     const u64 total = __shfl_sync(0xffffffffu, inc, 31);
                     pos += (u32)(total < room ? total : room);
@@ -804,7 +807,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     // =============================================================================================
     // the solver warp
     // =============================================================================================
-    u32 n_assigned = 0, n_segments = 0;
+    u32 n_assigned = 0, n_segments = 0, n_visits = 0, n_fast = 0;
     bool seg_overflow = false;
     if (warp != 0) {
         for (;;) {
@@ -903,6 +906,132 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         }
                     }
                 }
+                if (plain && (packed || skip_sat) && !level_packed) {
+                    // ---- lean first-fit over ALL remaining groups (no more packing can happen): the frontier tile's free
+                    //      vectors stay in registers (lane = worker) from group to group, the next group's request is
+                    //      prefetched, and the only work on the group-to-group dependency chain is fit -> ballot -> take.
+                    u32 cur_tile = 0xFFFFFFFFu;
+                    bool dirty = false;
+                    AT fr[RT];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) fr[r] = 0;
+                    uint2 ge_n = s_glist[li];
+                    u32 c_n = s_gcl[li] & 0xFFFFu;
+                    Var dv_n = classes[c_n].v[0];
+                    u32 front_n = s_front[c_n];
+                    for (u32 e = li; e < n_list; ++e) {
+                        const uint2 ge = ge_n;
+                        const u32 c = c_n;
+                        Var dv = dv_n;
+                        dv.all_mask = 0;                                         // plain tick: lets the compiler drop the `All` arm
+                        const u32 tile0 = front_n;
+                        if (e + 1 < n_list) {
+                            ge_n = s_glist[e + 1];
+                            c_n = s_gcl[e + 1] & 0xFFFFu;
+                            dv_n = classes[c_n].v[0];
+                            front_n = s_front[c_n];
+                        }
+                        const u32 g = ge.x, n_all = ge.y;
+                        u32 remaining = n_all, tile = tile0, f = tile0;
+                        const u32 seg_lo = seg_base;
+                        u32 seg_cur = seg_base;
+                        bool front = true;
+                        while (remaining && tile < n_tiles) {
+                            const u32 w = tile * 32 + lane;
+                            if (tile != cur_tile) {
+                                if (dirty) {
+                                    const u32 wo = cur_tile * 32 + lane;
+                                    if (wo < W) {
+#pragma unroll
+                                        for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
+                                    }
+                                }
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) fr[r] = w < W ? s_fr[(size_t)w * RT + r] : 0;
+                                cur_tile = tile;
+                                dirty = false;
+                            }
+                            ++n_visits;
+                            const u64 cnt = fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
+                            const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
+                            u32 take = 0, exc = 0, handed = 0;
+                            if (hasm) {
+                                const u32 first = (u32)__ffs(hasm) - 1;
+                                const u32 fall = __shfl_sync(0xffffffffu, cnt >= remaining ? 1u : 0u, first);
+                                if (fall) {
+                                    take = lane == first ? remaining : 0;
+                                    handed = remaining;
+                                } else if (remaining <= 0x03FFFFFFu) {
+                                    u32 inc = (u32)cnt;
+#pragma unroll
+                                    for (int d = 1; d < 32; d <<= 1) {
+                                        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                        if ((int)lane >= d) inc += y;
+                                    }
+                                    exc = inc - (u32)cnt;
+                                    if (cnt && exc < remaining) take = min((u32)cnt, remaining - exc);
+                                    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+                                    handed = min(total, remaining);
+                                } else {
+                                    u64 inc = cnt;
+#pragma unroll
+                                    for (int d = 1; d < 32; d <<= 1) {
+                                        const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                        if ((int)lane >= d) inc += y;
+                                    }
+                                    const u64 e64 = inc - cnt;
+                                    exc = (u32)(e64 < remaining ? e64 : remaining);
+                                    if (cnt && e64 < remaining) take = (u32)(cnt < remaining - e64 ? cnt : remaining - e64);
+                                    const u64 total = __shfl_sync(0xffffffffu, inc, 31);
+                                    handed = (u32)(total < remaining ? total : remaining);
+                                }
+                            }
+                            const u32 tkm = __ballot_sync(0xffffffffu, take != 0);
+                            if (take) {
+                                const u32 si = seg_cur + __popc(tkm & lt_mask);
+                                if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w; }
+                            }
+                            take_from<RT, AT>(fr, dv, take);                       // take == 0 leaves the lane as it is
+                            dirty |= tkm != 0;
+                            seg_cur += __popc(tkm);
+                            if (front) {
+                                const u32 alive = __ballot_sync(0xffffffffu, !(cnt < remaining && take == (u32)cnt));
+                                if (alive == 0) f = tile + 1; else front = false;
+                            }
+                            remaining -= handed;
+                            if (remaining) ++tile;
+                        }
+                        if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
+                        if (c_n == c) front_n = f;                               // the same class again (next level)
+                        const u32 k = n_all - remaining;
+                        u32 k_loc = k;
+                        if (before) {
+                            const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
+                            const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
+                            k_loc = k > bef ? k - bef : 0;
+                            k_loc = k_loc < loc ? k_loc : loc;
+                        }
+                        if (lane == 0) {
+                            GroupOut go;
+                            go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_cur - seg_lo;
+                            a.gout[g] = go;
+                        }
+                        out_base += k_loc;
+                        seg_base = seg_cur;
+                        if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+                    }
+                    if (dirty) {
+                        const u32 wo = cur_tile * 32 + lane;
+                        if (wo < W) {
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
+                        }
+                    }
+                    __syncwarp();
+                    n_fast += n_list - li;
+                    li = n_list;
+                    break;
+                }
                 // ---- the groups of the level, in order: first-fit (after what pack placed)
                 u32 region_end = seg_base;
                 if (level_packed) {
@@ -949,6 +1078,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         const bool last_round = vi + 1 == nv;
                         bool front = true;
                         for (u32 tile = s_front[c]; tile < n_tiles && remaining; ++tile) {
+                            ++n_visits;
                             const u32 w = tile * 32 + lane;
                             const bool in_pool = w < W;
                             const bool has = in_pool && !s_excl[w];
@@ -1166,10 +1296,10 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         h.dbg[1] = (unsigned long long)(t_prologue - t_counted);  // exchange + compaction + demand
         h.dbg[2] = (unsigned long long)(t_solved - t_prologue);   // the solver warp
         h.dbg[3] = (unsigned long long)(t_end - t_solved);        // emit (+ free vectors)
-        h.dbg[4] = n_list;
+        h.dbg[4] = (unsigned long long)n_list | ((unsigned long long)n_visits << 32);       // groups | tile visits
         h.dbg[5] = (unsigned long long)(t_end - t_start);
         h.dbg[6] = global_timer_ns() - gt_start;                  // the same interval in ns
-        h.dbg[7] = s_npacks;
+        h.dbg[7] = (unsigned long long)s_npacks | ((unsigned long long)n_fast << 32);      // pack commands | groups of the lean loop
         *a.hdr = h;
         if (a.hdr_host) *a.hdr_host = h;
         // the tick is over: every worker CTA has left its loops
