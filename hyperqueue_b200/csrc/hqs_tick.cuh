@@ -25,7 +25,7 @@ constexpr u32 TICK_WARPS = TICK_THREADS / 32;
 constexpr u32 EMIT_ROWS_MAX = 16;     // rows of 32 tasks per emit warp and chunk
 constexpr u32 EMIT_SEG_SMEM = 1024;   // count segments cached in shared memory by the emit step
 constexpr u32 CMD_PACK = 1, CMD_EMIT = 2, CMD_EXIT = 3;      // grid commands: cmd word = (sequence << 2) | type
-constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3, BLK_PIPE = 4;    // block commands inside the solver CTA
+constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3;    // block commands inside the solver CTA
 constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4;
 constexpr u32 SM_NONE = 0xFFFFFFFFu;
 constexpr u32 MU_MAX_PASSES = 8;      // restarts of the min-utilisation rule before the remaining violators are dropped
@@ -43,7 +43,7 @@ struct TickSync {
 // offsets into the solver CTA's dynamic shared memory (SM_NONE: the array stays in global memory)
 struct TickSmem {
     u32 fr, rem, unt, remtime, excl, td, frontier, glist, gcl;     // always staged
-    u32 classes, vorder, blocked, bef, loc, pipe;                  // optional
+    u32 classes, vorder, blocked, bef, loc;                        // optional
 };
 
 struct TickArgs {
@@ -74,8 +74,6 @@ struct TickArgs {
     GroupOut* gout;          // [G]
     u32* seg_cum;            // [SEG_CAP] inclusive end rank of the segment inside its group
     u32* seg_wv;             // [SEG_CAP] worker | variant << 16
-    u32* stage_cum;          // [SEG_CAP] staging of the pipelined first-fit: segments of list entry e at [e * W, e * W + W)
-    u32* stage_wv;
     u64* free_after;         // [W][R] device copy
     TickHeaderOut* hdr;      // device copy
     TickHeaderOut* hdr_host; // pinned host mirror: header followed by free_after [W][R] (read by hqs_tick_fetch)
@@ -670,142 +668,6 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             bar_named(2, TICK_THREADS);
             return;
         }
-        if (cmd == BLK_PIPE) {
-            // ---- pipelined first-fit of a plain, unsaturated tick over the entries [e0, n_list): lane = worker (two workers
-            //      per lane beyond 512), every warp a stage of 32 (64) workers.  At step t lane l handles entry t - l: it
-            //      receives (tasks still unplaced, segments so far) from lane l - 1, takes what fits, passes the rest on —
-            //      the quotients do not wait for the neighbour, only the final min() does.  Warps hand over through a
-            //      shared-memory queue, one 64-bit word per (warp, entry).
-            const u32 e0 = s_blk[1], seg0 = s_blk[3], out0 = s_blk[6];
-            const u32 n_it = n_list - e0;
-            const u32 kw = W > 32 * TICK_WARPS ? 2u : 1u;
-            const u32 n_pw = (W + 32 * kw - 1) / (32 * kw);
-            unsigned long long* s_q = reinterpret_cast<unsigned long long*>(smem + a.sm.pipe);     // [n_pw][n_it]
-            for (u32 i = tid; i < n_pw * n_it; i += blockDim.x) s_q[i] = ~0ull;
-            bar_named(2, TICK_THREADS);
-            if (warp < n_pw) {
-                AT fr[2][RT];
-                const u32 wbase = (warp * 32 + lane) * kw;
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) fr[k][r] = ((u32)k < kw && wbase + k < W) ? s_fr[(size_t)(wbase + k) * RT + r] : 0;
-                u32 rem_out = 0, ns_out = 0;
-                const u32 T = n_it + 31;
-                for (u32 t = 0; t < T; ++t) {
-                    const int i = (int)t - (int)lane;
-                    const bool active = i >= 0 && i < (int)n_it;
-                    u32 rem_in = __shfl_up_sync(0xffffffffu, rem_out, 1);
-                    u32 ns_in = __shfl_up_sync(0xffffffffu, ns_out, 1);
-                    if (lane == 0 && t < n_it) {
-                        if (warp == 0) { rem_in = s_glist[e0 + t].y; ns_in = 0; }
-                        else {
-                            volatile unsigned long long* qp = s_q + (size_t)(warp - 1) * n_it + t;
-                            unsigned long long v;
-                            const long long t0 = clock64();
-                            while ((v = *qp) == ~0ull) {
-                                if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { s_err = 2; v = 0; break; }
-                            }
-                            rem_in = (u32)v; ns_in = (u32)(v >> 32);
-                        }
-                    }
-                    if (active) {
-                        const u32 e = e0 + (u32)i;
-                        const u32 c = s_gcl[e] & 0xFFFFu, n_all = s_glist[e].y;
-                        Var dv = classes[c].v[0];
-                        dv.all_mask = 0;                                         // plain tick
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            if ((u32)k < kw && rem_in) {
-                                const u32 cnt = (u32)fit_count<RT>(fr[k], 0u, dv, rem_in);   // lanes beyond the pool hold zeros: 0
-                                if (cnt) {
-                                    const size_t si = (size_t)e * W + ns_in;
-                                    a.stage_cum[si] = (n_all - rem_in) + cnt;
-                                    a.stage_wv[si] = wbase + k;
-                                    take_from<RT, AT>(fr[k], dv, cnt);
-                                    rem_in -= cnt;
-                                    ns_in += 1;
-                                }
-                            }
-                        }
-                        rem_out = rem_in; ns_out = ns_in;
-                        if (lane == 31) {
-                            volatile unsigned long long* qo = s_q + (size_t)warp * n_it + (u32)i;
-                            *qo = (unsigned long long)rem_out | ((unsigned long long)ns_out << 32);
-                        }
-                    }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if ((u32)k < kw && wbase + k < W) {
-#pragma unroll
-                        for (int r = 0; r < RT; ++r) s_fr[(size_t)(wbase + k) * RT + r] = fr[k][r];
-                    }
-            }
-            __threadfence_block();
-            bar_named(2, TICK_THREADS);
-            // ---- per entry: tasks placed and segments; exclusive scans give the output offsets and the dense segment
-            //      positions; segments move from the staging area to their place
-            const u32 per = (n_it + blockDim.x - 1) / blockDim.x;
-            const u32 i_lo = min(tid * per, n_it), i_hi = min(i_lo + per, n_it);
-            const unsigned long long* fin = s_q + (size_t)(n_pw - 1) * n_it;
-            u32 sum_k = 0, sum_s = 0;
-            for (u32 i = i_lo; i < i_hi; ++i) {
-                const u32 e = e0 + i, g = s_glist[e].x, n_all = s_glist[e].y;
-                const unsigned long long v = fin[i];
-                const u32 k = n_all - (u32)v;
-                u32 k_loc = k;
-                if (before) {
-                    const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
-                    const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
-                    k_loc = k > bef ? k - bef : 0;
-                    k_loc = k_loc < loc ? k_loc : loc;
-                }
-                sum_k += k_loc;
-                sum_s += (u32)(v >> 32);
-            }
-            u32 inc_k = sum_k, inc_s = sum_s;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 yk = __shfl_up_sync(0xffffffffu, inc_k, d), ys = __shfl_up_sync(0xffffffffu, inc_s, d);
-                if ((int)lane >= d) { inc_k += yk; inc_s += ys; }
-            }
-            if (lane == 31) { s_red[warp] = inc_k; s_red[TICK_WARPS + warp] = inc_s; }
-            bar_named(2, TICK_THREADS);
-            u32 off_k = out0 + inc_k - sum_k, off_s = seg0 + inc_s - sum_s, tot_k = 0, tot_s = 0;
-            for (u32 w2 = 0; w2 < TICK_WARPS; ++w2) {
-                const u32 ck = (u32)s_red[w2], cs = (u32)s_red[TICK_WARPS + w2];
-                if (w2 < warp) { off_k += ck; off_s += cs; }
-                tot_k += ck; tot_s += cs;
-            }
-            for (u32 i = i_lo; i < i_hi; ++i) {
-                const u32 e = e0 + i, g = s_glist[e].x, n_all = s_glist[e].y;
-                const unsigned long long v = fin[i];
-                const u32 k = n_all - (u32)v, ns = (u32)(v >> 32);
-                u32 k_loc = k;
-                if (before) {
-                    const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
-                    const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
-                    k_loc = k > bef ? k - bef : 0;
-                    k_loc = k_loc < loc ? k_loc : loc;
-                }
-                for (u32 q = 0; q < ns; ++q)
-                    if (off_s + q < SEG_CAP) {
-                        a.seg_cum[off_s + q] = a.stage_cum[(size_t)e * W + q];
-                        a.seg_wv[off_s + q] = a.stage_wv[(size_t)e * W + q];
-                    }
-                GroupOut go;
-                go.k = k; go.out_off = off_k; go.seg_lo = off_s; go.seg_n = ns;
-                a.gout[g] = go;
-                off_k += k_loc;
-                off_s += ns;
-            }
-            if (tid == 0) { s_blk[6] = out0 + tot_k; s_blk[7] = seg0 + tot_s; }
-            __threadfence();
-            bar_named(2, TICK_THREADS);
-            return;
-        }
         // ---- BLK_PACK: the level [li, lj) is saturated
         const u32 li = s_blk[1], lj = s_blk[2], region0 = s_blk[3];
         const u32 ng = lj - li;
@@ -1043,19 +905,6 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             level_packed = s_err == 0;
                         }
                     }
-                }
-                if (plain && skip_sat && !packed && a.sm.pipe != SM_NONE) {
-                    // ---- plain and unsaturated: most groups get placed; the pipelined first-fit of all warps takes over
-                    if (lane == 0) { s_blk[0] = BLK_PIPE; s_blk[1] = li; s_blk[3] = seg_base; s_blk[6] = out_base; }
-                    __syncwarp();
-                    bar_named(1, TICK_THREADS);
-                    block_work(BLK_PIPE);
-                    out_base = s_blk[6];
-                    seg_base = s_blk[7];
-                    if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
-                    n_fast += n_list - li;
-                    li = n_list;
-                    break;
                 }
                 if (plain && (packed || skip_sat) && !level_packed) {
                     // ---- lean first-fit over ALL remaining groups (no more packing can happen): the frontier tile's free

@@ -117,8 +117,7 @@ struct hqs_ctx {
     bool sync_dirty = true;             // the counters must be zeroed before the next launch (first tick / after a failed one)
     u64* d_pk_fr = nullptr; u32* d_pk_quota = nullptr; u32* d_pk_taken = nullptr; u32* d_pk_cand = nullptr; u32* d_pk_meta = nullptr;
     u32* d_rem_scratch = nullptr; uint8_t* d_excl = nullptr;
-    u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr; u32* d_stage_cum = nullptr; u32* d_stage_wv = nullptr;
-    bool plain_classes = false;         // every class has one variant and no `All` entry
+    u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr;
     hqs_assignment* d_out = nullptr; u32 out_cap_dev = 0;
     TickHeaderOut* d_hdr = nullptr;
     u64* d_free_after = nullptr;
@@ -292,8 +291,6 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
     if (!ctx->d_seg_cum) {
         CU(cudaMalloc(&ctx->d_seg_cum, SEG_CAP * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_seg_wv, SEG_CAP * sizeof(u32)));
-        CU(cudaMalloc(&ctx->d_stage_cum, SEG_CAP * sizeof(u32)));
-        CU(cudaMalloc(&ctx->d_stage_wv, SEG_CAP * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_hdr, sizeof(TickHeaderOut)));
         CU(cudaMalloc(&ctx->d_free_after, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
         CU(cudaMalloc(&ctx->d_sync, sizeof(TickSync)));
@@ -541,7 +538,6 @@ TickArgs base_args(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay
     a.table = ctx->d_table;
     a.gout = ctx->d_gout;
     a.seg_cum = ctx->d_seg_cum; a.seg_wv = ctx->d_seg_wv;
-    a.stage_cum = ctx->d_stage_cum; a.stage_wv = ctx->d_stage_wv;
     a.free_after = ctx->d_free_after;
     a.hdr = ctx->d_hdr;
     a.hdr_host = reinterpret_cast<TickHeaderOut*>(ctx->h_hdr_dev);
@@ -580,12 +576,6 @@ size_t solver_layout(const hqs_ctx* ctx, TickArgs& a, size_t budget, bool sharde
     a.sm.bef = opt((size_t)n_pos * 4, sharded);
     a.sm.loc = a.sm.bef != SM_NONE ? opt((size_t)n_pos * 4, sharded) : SM_NONE;
     if (a.sm.loc == SM_NONE) a.sm.bef = SM_NONE;
-    // queues of the pipelined first-fit (plain ticks): one 64-bit word per (pipeline warp, list entry); its staging area
-    // holds W segments per entry
-    const u32 kw = W > 32 * TICK_WARPS ? 2u : 1u, n_pw = (W + 32 * kw - 1) / (32 * kw);
-    const bool may_pipe = ctx->plain_classes && a.blocked == nullptr && !a.any_time_limit && a.min_util == nullptr &&
-                          (u64)n_pos * W <= SEG_CAP && a.sm.classes != SM_NONE;
-    a.sm.pipe = opt((size_t)n_pw * n_pos * 8, may_pipe);
     a.smem_solver = (u32)o;
     return o;
 }
@@ -732,7 +722,7 @@ void hqs_destroy(hqs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* dev_ptrs[] = {ctx->d_classes, ctx->d_classes32, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
                         ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
-                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_rem_scratch, ctx->d_excl, ctx->d_stage_cum, ctx->d_stage_wv, ctx->d_seg_cum,
+                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_rem_scratch, ctx->d_excl, ctx->d_seg_cum,
                         ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
                         ctx->d_pk_quota, ctx->d_pk_taken, ctx->d_pk_cand, ctx->d_pk_meta};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
@@ -839,9 +829,6 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
         }
     }
     ctx->narrow_classes = narrow_ok;
-    ctx->plain_classes = true;
-    for (u32 c = 0; c < n_classes; ++c)
-        if (classes[c].n_variants != 1 || classes[c].variants[0].all_mask) ctx->plain_classes = false;
     if (blob32.size() > ctx->d_classes32_cap) {
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_classes32) CU(cudaFree(ctx->d_classes32));
