@@ -4,36 +4,41 @@
     python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
     python bench.py --impl reference --steps K --warmup W    # restated reference tick on the host CPU
 
-One "step" = one scheduler tick over one batch of synthetic input: BASELINE.json configs[1]
-(1M independent ready tasks x 256 workers x 4 resource kinds, one fractional; Q=16 request classes,
-Zipf(1.1) class mix, 8 priority levels), mode M1 of SURVEY.md §8(d): capacity >= demand, so every ready
-task is assigned in that one tick and value = tasks / tick time.
+One "step" = one scheduler tick over one batch of synthetic input, mode M1 of SURVEY.md §8(d): capacity >= demand, so
+every ready task is assigned in that one tick and value = tasks / tick time.
 
-  value     device-resident: the ready set already sits in HBM; the timed region holds K ticks on K
-            different contexts (252 MB of distinct task tables > the 126 MB L2, so no step re-reads a
-            warm table), each tick = upload of the worker state + count_k + solve_k + emit_k.
-  e2e       the same tick through the public C ABI with HOST buffers: hqs_ready_push (H2D of task,
-            class, priority arrays from pinned memory) + hqs_tick (D2H of the 8-byte assignments and the
-            free vectors) inside the timed region.
-  roofline  emit_k (the kernel with the most algorithmic HBM traffic) timed with CUDA events on the
-            context stream, against MEASURED_PEAKS.json; per-kernel times are in "kernels".
-  cpu_baseline  the oracle (restated reference tick, HiGHS 1.12.0) on a bounded sample of the same
-            workload, single-threaded like the reference (Rc<RefCell<Core>>).
+  N = 1   BASELINE.json configs[1] (cfg2): 1 M independent ready tasks x 256 workers x 4 resource kinds (one
+          fractional), Q = 16 request classes, Zipf(1.1) class mix, 8 priority levels.
+  N > 1   BASELINE.json configs[4] (cfg5) shape: 1024 workers, the task table block-sharded by handle over the ranks,
+          1.25 M tasks per GPU (10 M at N = 8), weak scaling.  The only exchange of a tick is the per-group count vector
+          (4 B x groups per rank): NVLink peer stores issued by the tick kernel itself (default), or an NCCL all-gather
+          between two kernel launches (--nccl-exchange).
 
-N > 1 GPUs: the task table is block-sharded by handle over the ranks; the only exchange is an NCCL
-all-gather of the per-group count vectors (16 KB) and the replicated deterministic solve (weak scaling:
-1M tasks per GPU).
+  value     device-resident: the ready set already sits in HBM; the timed region holds K ticks on K different contexts
+            (K + W distinct 12-15 MB task tables > the 126 MB L2, so no step re-reads a warm table); a tick = ONE
+            cooperative kernel (histogram, solve, emit) that reads the worker state from pinned host memory.
+  e2e       the same tick through the public C ABI with HOST buffers: hqs_ready_push (H2D of the task, class and
+            priority arrays from pinned memory) + hqs_tick (D2H of the 8-byte assignments and the free vectors) inside
+            the timed region.
+  roofline  the tick kernel (the only kernel of a step) against MEASURED_PEAKS.json: algorithmic bytes of SURVEY.md
+            §8(d)'s contract (36 B per assignment + the worker vectors) / the kernel's duration; the same with the
+            interned 20 B/task budget, and the kernel's phases, are reported next to it.
+  cpu_baseline / --impl reference   the oracle (restated reference tick, HiGHS 1.12.0) on the SAME workload, single-
+            threaded like the reference (Rc<RefCell<Core>>), with the reference's solver defaults relaxed to a 1 % MIP gap
+            and a 2 s cap (parity.ORACLE_FAST; `solver_hit_cap` says whether the cap was reached).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import traceback
 
 import numpy as np
 
@@ -41,12 +46,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_TASKS = 1_000_000
-N_WORKERS = 256
 N_CLASSES = 16
 FREE_SCALE = 1024
 METRIC = "assignments/sec on 1M ready tasks x 256 workers x 4 resource kinds"
-WORKLOAD = "cfg2-M1: 1M independent tasks, 256 workers, R=4 (gpus fractional), Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"
+CFG2 = {"name": "cfg2-M1", "tasks_per_gpu": 1_000_000, "workers": 256,
+        "workload": "cfg2-M1: 1M independent tasks, 256 workers, R=4 (gpus fractional), Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"}
+CFG5 = {"name": "cfg5-M1", "tasks_per_gpu": 1_250_000, "workers": 1024,
+        "workload": "cfg5-M1: 1.25M independent tasks per GPU (10M at 8 GPUs) block-sharded by handle, 1024 workers, R=4 (gpus fractional), "
+                    "Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"}
+BYTES_CONTRACT = 36      # V*R*4 amounts + 8 priority + 4 class/flags read, 8 written per assignment (cfg2, cfg5)
+BYTES_INTERNED = 20      # what the path moves with interned classes: 4 key read (count) + 4 key read (emit) + 8 assignment + 4 key write-back
 
 
 def _peaks():
@@ -93,50 +102,66 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_workload(n_tasks: int, seed: int, n_workers: int = N_WORKERS, free_scale: int = FREE_SCALE):
+def make_workload(cfg: dict, seed: int, n_classes: int = N_CLASSES, free_scale: int = FREE_SCALE, **kw):
     import workloads as WL          # synthetic inputs only; does not import the oracle
-    return WL.make_independent(n_tasks, n_workers, N_CLASSES, seed=seed, free_scale=free_scale)
+    return WL.make_independent(cfg["tasks_per_gpu"], cfg["workers"], n_classes, seed=seed, free_scale=free_scale, **kw)
+
+
+def config_block(cfg: dict, world: int, **extra) -> dict:
+    """The `config` object of the JSON line: identical keys and values in the CUDA arm and in the reference arm."""
+    c = {"workload": cfg["workload"], "name": cfg["name"], "tasks_per_gpu": cfg["tasks_per_gpu"], "workers": cfg["workers"],
+         "classes": N_CLASSES, "pool_free_scale": FREE_SCALE}
+    c.update(extra)
+    return c
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle on the host CPU
+# reference arm / cpu baseline: the oracle on the host CPU, same workload
 # ---------------------------------------------------------------------------------------------------
-def oracle_step(sample: int, seed: int):
-    """One M1 tick of the restated reference on a `sample`-task cut of the workload.  Returns
-    (assignments, seconds) — queue construction is outside the timed region, like the HBM-resident
-    ready set of the CUDA arm."""
+def oracle_step(cfg: dict, seed: int):
+    """One M1 tick of the restated reference on the workload.  Returns (assignments, seconds, solver hit its cap) —
+    queue construction is outside the timed region, like the HBM-resident ready set of the CUDA arm."""
     import parity as P
-    wl = make_workload(sample, seed)
+    wl = make_workload(cfg, seed)
     core = P.oracle_core(wl)
     core.scheduler_state.config.proactive_filling_max = 0
     t0 = time.perf_counter()
     mapping = core.schedule_mapping(0.0, **P.ORACLE_FAST)
     dt = time.perf_counter() - t0
-    return mapping.n_assigned(), dt
+    info = getattr(core, "last_solver_info", None) or {}
+    return mapping.n_assigned(), dt, bool(info.get("hit_time_limit", False))
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.ref_sample
-    for i in range(args.warmup):
-        oracle_step(sample, 100 + i)
-    n_tot, t_tot = 0, 0.0
+    cfg = CFG2 if args.gpus == 1 else CFG5
+    for i in range(min(args.warmup, 1)):            # the CPU arm has no caches to warm beyond the first import
+        oracle_step(cfg, 100 + i)
+    n_tot, t_tot, capped, timed = 0, 0.0, 0, 0
+    t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        n, dt = oracle_step(sample, i)
+        n, dt, cap = oracle_step(cfg, i)
         n_tot += n
         t_tot += dt
+        capped += int(cap)
+        timed += 1
+        # every step is the FULL workload (6-20 s of CPU work each); the run is bounded by wall-clock instead of by
+        # a smaller sample: steps beyond the budget are not run and `steps_timed` says how many were
+        if time.perf_counter() - t_wall0 > args.ref_budget_s and timed >= 3:
+            break
     value = n_tot / t_tot if t_tot > 0 else 0.0
     desc = {"value": value, "unit": "assignments/s", "cores": 1, "kind": "port",
-            "sample": f"{sample}-task cut of the workload per step (same class mix, 256 workers, one M1 tick); "
-                      f"oracle = restated reference tick (Python + HiGHS 1.12.0 via scipy, 1 % MIP gap, 2 s cap); "
-                      f"host has {os.cpu_count()} cores, 1 used (the reference tick is single-threaded)"}
+            "sample": f"the full workload of one GPU per step ({cfg['tasks_per_gpu']} tasks, {cfg['workers']} workers, one M1 tick; the "
+                      f"reference assigns at most 1024 tasks of a class per worker and tick, workerload.rs:12); oracle = restated "
+                      f"reference tick (Python + HiGHS 1.12.0 via scipy, 1 % MIP gap, 2 s cap, cap reached in {capped} of "
+                      f"{timed} timed steps); host has {os.cpu_count()} cores, 1 used (the reference tick is single-threaded)"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / max(args.steps, 1),
+        "steps": args.steps, "steps_timed": timed, "warmup": args.warmup, "ms_per_step": 1000.0 * t_tot / max(timed, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_sample_tasks": sample},
+        "config": config_block(cfg, args.gpus),
         "cpu_baseline": desc,
         "e2e": {"value": value, "unit": "assignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -145,7 +170,43 @@ def run_reference(args) -> None:
 # ---------------------------------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------
-def run_cuda(args) -> None:
+def device_m1(P, L, wl, n_ticks: int, device: int, stream, profile: bool = False):
+    """n_ticks M1 ticks of one workload on one context, re-armed in between; returns (per-tick kernel ms list, stats)."""
+    import torch
+    s = P.gpu_scheduler(wl, device=device)
+    s._check(s._lib.hqs_set_profile(s._ctx, 1))
+    out = []
+    for _ in range(n_ticks + 1):
+        s.free = wl.worker_free.copy()
+        m = s.run_scheduling()
+        ms = (C.c_float * 4)()
+        s._check(s._lib.hqs_get_kernel_ms(s._ctx, ms))
+        out.append((float(ms[3]), m.n_assigned()))
+        s.rearm()
+    st = s.stats()
+    s.close()
+    return out[1:], st
+
+
+def drain(P, wl, device: int, max_ticks: int = 20000, dag: bool = False):
+    """Mode M2: zero-duration drain through the public call (tick, finish everything, return resources)."""
+    s = P.gpu_scheduler(wl, device=device)
+    t0 = time.perf_counter()
+    left, ticks = wl.n_tasks, 0
+    while left > 0 and ticks < max_ticks:
+        m = s.run_scheduling()
+        if m.n_assigned() == 0:
+            break
+        left -= m.n_assigned()
+        ticks += 1
+        s.tasks_finished(m.assignments["task"], propagate=dag)
+    dt = time.perf_counter() - t0
+    s.close()
+    return {"value": (wl.n_tasks - left) / dt, "unit": "assignments/s", "ticks": ticks, "seconds": dt,
+            "ms_per_tick": 1000.0 * dt / max(ticks, 1), "assigned": wl.n_tasks - left}
+
+
+def run_cuda(args) -> dict:
     import torch
     import torch.distributed as dist
     import workloads as P           # the CUDA arm never imports oracle/ (only the cpu_baseline leg below does)
@@ -158,30 +219,31 @@ def run_cuda(args) -> None:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     K, Wm = args.steps, args.warmup
     n_ctx = K + Wm
+    cfg = CFG2 if world == 1 else CFG5
+    n_tasks, n_workers = cfg["tasks_per_gpu"], cfg["workers"]
 
     # one stream shared by every context so the ticks serialise and torch events time them
     stream = torch.cuda.Stream(device=dev)
-    # one class table / worker pool for every rank; M1 = "every ready task is assignable in one tick", so the pool's
-    # free capacity grows with the number of ranks (weak scaling: 1 M tasks per GPU against world x the capacity)
-    wl = make_workload(N_TASKS, seed=0, free_scale=FREE_SCALE * world * int(os.environ.get("HQS_BENCH_POOL_MULT", "1")))
+    # one class table / worker pool for every rank; the ranks' task tables differ (rolled class / priority arrays)
+    wl = make_workload(cfg, seed=0)
     if rank:
         wl.task_class = np.roll(wl.task_class, rank * 104729)
-        wl.task_user_priority = np.roll(wl.task_user_priority, rank * 15485863 % N_TASKS)
+        wl.task_user_priority = np.roll(wl.task_user_priority, rank * 15485863 % n_tasks)
     prio = priority_from_user(wl.task_user_priority)
-    handles = np.arange(N_TASKS, dtype=np.uint32)
+    task_handles = np.arange(n_tasks, dtype=np.uint32)
     scheds = []
     for i in range(n_ctx):
         s = P.gpu_scheduler(wl, add_tasks=False, device=local_rank)
         s._sync_classes()
         s._check(s._lib.hqs_set_stream(s._ctx, C.c_void_p(stream.cuda_stream)))
-        # distinct device tables; rotate the class/priority arrays so the tables differ
         lv = np.ascontiguousarray(np.unique(prio))
         s._check(s._lib.hqs_levels_add(s._ctx, lv.size, L.ptr(lv)))      # same level numbering on every rank
-        s.add_ready_tasks(handles, np.roll(wl.task_class, i * 7919), np.roll(prio, i * 7919))
+        # distinct device tables: rotate the class / priority arrays
+        s.add_ready_tasks(task_handles, np.roll(wl.task_class, i * 7919), np.roll(prio, i * 7919))
         scheds.append(s)
     torch.cuda.synchronize()
 
@@ -189,20 +251,21 @@ def run_cuda(args) -> None:
     free = np.ascontiguousarray(wl.worker_free)
     total = np.ascontiguousarray(wl.worker_total)
     lib = scheds[0]._lib
+    p2p = world > 1 and not args.nccl_exchange
 
-    def launch(s, counts=None):
-        s._check(lib.hqs_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
+    def launch(s):
+        s._check(lib.hqs_tick_launch(s._ctx, n_workers, L.ptr(workers), L.ptr(free), L.ptr(total), None, n_tasks))
 
     def sharded_tick(s, bufs):
         if p2p:
-            # fused: count -> NVLink peer stores of the count vector + release flag -> the solver acquires the
-            # flags and sums the vectors on the device -> local emit.  No host collective on the data path.
-            s._check(lib.hqs_shard_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
+            # fused: histogram -> NVLink peer stores of the count vector + release flags -> the solver acquires the flags
+            # and sums the vectors -> local emit, all inside ONE kernel.  No host collective on the data path.
+            s._check(lib.hqs_shard_tick_launch(s._ctx, n_workers, L.ptr(workers), L.ptr(free), L.ptr(total), None, n_tasks))
             return
         # count locally, all-gather the count vectors (NCCL), replicated solve, local emit
         cnt, gathered = bufs
         ng = C.c_uint32(0)
-        s._check(lib.hqs_shard_count(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None,
+        s._check(lib.hqs_shard_count(s._ctx, n_workers, L.ptr(workers), L.ptr(free), L.ptr(total), None,
                                      C.c_void_p(cnt.data_ptr()), cnt.numel(), C.byref(ng)))
         with torch.cuda.stream(stream):
             dist.all_gather_into_tensor(gathered, cnt)
@@ -210,20 +273,16 @@ def run_cuda(args) -> None:
             allc = g2.sum(0, dtype=torch.int64).to(torch.int32)
             before = g2[:rank].sum(0, dtype=torch.int64).to(torch.int32) if rank else torch.zeros_like(cnt)
         s._sh = (allc, before)
-        s._check(lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(allc.data_ptr()), C.c_void_p(before.data_ptr()), N_TASKS))
+        s._check(lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(allc.data_ptr()), C.c_void_p(before.data_ptr()), n_tasks))
 
-    p2p = world > 1 and not args.nccl_exchange
     if p2p:
         from hyperqueue_b200.sharded import gather_peer_handles, open_and_attach
         ok = 1
+        pending = [gather_peer_handles(s, rank, world) for s in scheds]          # collective: every rank, every context
         try:
-            pending = [gather_peer_handles(s, rank, world) for s in scheds]      # collective: every rank, every context
-        except Exception as e:
-            raise SystemExit(f"[bench] exchange-buffer set-up failed on rank {rank}: {e}")
-        try:
-            for s, (own, handles) in zip(scheds, pending):                      # local: may fail without hanging the others
-                open_and_attach(s, rank, world, own, handles)
-                s._check(lib.hqs_tick_reserve(s._ctx, N_WORKERS, N_TASKS, 0))
+            for s, (own, ipc_handles) in zip(scheds, pending):                   # local: may fail without hanging the others
+                open_and_attach(s, rank, world, own, ipc_handles)
+                s._check(lib.hqs_tick_reserve(s._ctx, n_workers, n_tasks, 0))
         except Exception as e:          # e.g. CUDA IPC not permitted in this container: every rank falls back together
             print(f"[bench] rank {rank}: peer-to-peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
             ok = 0
@@ -251,10 +310,10 @@ def run_cuda(args) -> None:
     # ---- every context runs one untimed tick first (device buffers are allocated on the first tick),
     #      then its ready set is re-armed on the device
     out_n = C.c_uint32(0)
-    tmp_out = np.zeros(N_TASKS, dtype=L.assignment_dtype)
+    tmp_out = np.zeros(n_tasks, dtype=L.assignment_dtype)
     for s in scheds:
         step(s)
-        s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(tmp_out), C.byref(out_n), None))
+        s._check(lib.hqs_tick_fetch(s._ctx, n_tasks, L.ptr(tmp_out), C.byref(out_n), None))
         s._check(lib.hqs_ready_rearm(s._ctx))
     barrier()
     # ---- warm-up, then the timed region: exactly K steps, events on the launching stream -----------
@@ -272,14 +331,15 @@ def run_cuda(args) -> None:
     barrier()
     t_host = time.perf_counter() - t_host0
     ms_total = ev0.elapsed_time(ev1)
-    launches_timed = (4 if p2p else 3) * K            # count_k, (xchg_k,) solve_k, emit_k per step
-    # every step must have assigned every task
+    launches_timed = K if (world == 1 or p2p) else 2 * K            # tick_k per step (NCCL variant: count_only_k + tick_k)
+    # every step must have assigned every task of the rank
+    n_done_local = 0
     for i in range(K):
         s = scheds[Wm + i]
-        s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(tmp_out), C.byref(out_n), None))
+        s._check(lib.hqs_tick_fetch(s._ctx, n_tasks, L.ptr(tmp_out), C.byref(out_n), None))
+        n_done_local = int(out_n.value)
         if world == 1:
-            assert out_n.value == N_TASKS, f"step {i}: {out_n.value} of {N_TASKS} tasks assigned"
-    n_done_local = N_TASKS if world == 1 else int(out_n.value)
+            assert out_n.value == n_tasks, f"step {i}: {out_n.value} of {n_tasks} tasks assigned"
 
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -289,143 +349,157 @@ def run_cuda(args) -> None:
         dist.all_reduce(n_all)
         n_per_step = int(n_all.item())
     else:
-        n_per_step = N_TASKS
+        n_per_step = n_tasks
     ms_per_step = ms_total / K
     value = n_per_step / (ms_per_step / 1000.0)
 
-    # ---- per-kernel device times (profiled pass, same workload, re-armed tables) ----------------
-    kernels = {}
-    if world == 1:
-        acc = np.zeros(4)
-        reps = 0
-        for i in range(K):
-            s = scheds[Wm + i]
-            s._check(lib.hqs_ready_rearm(s._ctx))
-            s._check(lib.hqs_set_profile(s._ctx, 1))
-        torch.cuda.synchronize()
-        for i in range(K):
-            s = scheds[Wm + i]
-            launch(s)
-            torch.cuda.synchronize()
-            ms = (C.c_float * 4)()
-            s._check(lib.hqs_get_kernel_ms(s._ctx, ms))
-            acc += np.array(list(ms))
-            reps += 1
-            s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(tmp_out), C.byref(out_n), None))
-        acc /= max(reps, 1)
-        st = scheds[Wm].stats()
-        peak, peak_src = _peaks()
-        bytes_count = 4.0 * N_TASKS
-        bytes_emit = (4.0 + 8.0 + 4.0) * N_TASKS          # key read + assignment write + key write-back
-        kernels = {
-            "count_k": {"ms": acc[0], "algorithmic_bytes": bytes_count, "GBps": bytes_count / acc[0] / 1e6},
-            "solve_k": {"ms": acc[1], "groups": st["n_groups"], "note": "one CTA, latency-bound sequential first-fit; no HBM stream"},
-            "emit_k": {"ms": acc[2], "algorithmic_bytes": bytes_emit, "GBps": bytes_emit / acc[2] / 1e6},
-            "sum_ms": acc[3],
-        }
-        achieved = bytes_emit / acc[2] / 1e6
-        traffic = None      # dram read + write bytes of one emit_k launch from the committed ncu --set full capture
-        mp = os.path.join(ROOT, "profiles", "r1_ncu_metrics.json")
-        if os.path.exists(mp):
-            m = json.load(open(mp)).get("emit_k")
-            if m and m.get("dram_bytes_read") is not None:
-                traffic = m["dram_bytes_read"] + (m.get("dram_bytes_write") or 0.0)
-        roofline = {"bound": "hbm", "kernel": "emit_k", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "bytes_per_task": 16, "note": "interned classes: 4 B key read + 8 B assignment + 4 B key write-back per task "
-                                                  "(SURVEY §8(d) budgets 36 B/task for un-interned per-task amounts)",
-                    "tick_frac_of_hbm": ((4.0 + 16.0) * N_TASKS / (ms_per_step / 1000.0) / 1e9) / peak}
-    else:
-        roofline = None
+    # ---- phases of the tick kernel (profiled pass, same workload, re-armed tables) -------------------
+    acc = np.zeros(4)
+    for i in range(K):
+        s = scheds[Wm + i]
+        s._check(lib.hqs_ready_rearm(s._ctx))
+        s._check(lib.hqs_set_profile(s._ctx, 1))
+    barrier()
+    for i in range(K):
+        s = scheds[Wm + i]
+        step(s)
+        s._check(lib.hqs_tick_fetch(s._ctx, n_tasks, L.ptr(tmp_out), C.byref(out_n), None))
+        ms = (C.c_float * 4)()
+        s._check(lib.hqs_get_kernel_ms(s._ctx, ms))
+        acc += np.array(list(ms))
+    acc /= K
+    st = scheds[Wm].stats()
+    peak, peak_src = _peaks()
+    worker_bytes = 2.0 * n_workers * 4 * 8
+    bytes_contract = BYTES_CONTRACT * n_tasks + worker_bytes        # per launch (per GPU)
+    bytes_interned = BYTES_INTERNED * n_tasks + worker_bytes
+    kernel_ms = ms_per_step if (world == 1 or p2p) else float(acc[3])
+    achieved = bytes_contract / kernel_ms / 1e6
+    traffic = None          # dram read + write bytes of one tick_k launch from the committed ncu --set full capture
+    mp = os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")
+    if os.path.exists(mp):
+        m = json.load(open(mp)).get("tick_k")
+        if m and m.get("dram_bytes_read") is not None:
+            traffic = m["dram_bytes_read"] + (m.get("dram_bytes_write") or 0.0)
+    roofline = {"bound": "hbm", "kernel": "tick_k (the one kernel of a tick: histogram + solve + emit)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_assignment": BYTES_CONTRACT,
+                "algorithmic_bytes_per_launch": bytes_contract,
+                "kernel_ms": kernel_ms,
+                "interned": {"bytes_per_assignment": BYTES_INTERNED, "achieved": bytes_interned / kernel_ms / 1e6,
+                             "frac": bytes_interned / kernel_ms / 1e6 / peak,
+                             "note": "classes are interned (ResourceRqId), so the path itself moves 4 B key (histogram) + 4 B key "
+                                     "(emit, L2 hit) + 8 B assignment + 4 B key write-back per task"},
+                "note": "SURVEY.md §8(d) contract: 36 B per assignment (un-interned amounts 16 + priority 8 + class 4 read, 8 written) "
+                        "+ 2*W*R*8 B of worker vectors per tick; duration = CUDA events on the launching stream over the timed region / K"}
+    kernels = {"tick_k": {"ms": float(acc[3]), "phases_ms": {"stage+histogram": float(acc[0]), "exchange+compact+solve": float(acc[1]),
+                                                             "emit": float(acc[2])},
+                          "groups": st["n_groups"], "segments": st["n_segments"],
+                          "note": "phases as seen by the solver CTA's clock, scaled to the event-timed kernel duration; the solve is one "
+                                  "warp walking the non-empty groups (latency-bound), histogram and emit stream the task table"}}
 
-    # ---- mode M2: zero-duration drain of the same task set with REAL capacities
-    #      (256 workers x {128 cpus, 8 gpus, 512 GiB, 2048 GiB}); every tick goes through the public call
-    drain = None
-    if rank == 0 and world == 1 and not args.no_drain:
-        wl2 = make_workload(N_TASKS, seed=0, free_scale=1)
-        s2 = P.gpu_scheduler(wl2, device=local_rank)
-        s2.run_scheduling(); s2.rearm(); s2.free = wl2.worker_free.copy()          # allocate, then re-arm
-        torch.cuda.synchronize()
+    extra = {}
+    # ---- mode M2: zero-duration drains with REAL capacities, every tick through the public call;
+    #      class-pool sweep and seeds (N = 1 only)
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra["drain_m2_cfg2"] = dict(drain(P, make_workload(cfg, seed=0, free_scale=1), local_rank),
+                                      note="cfg2-M2: 1M tasks, 256 workers x {128 cpus, 8 gpus, 512 GiB, 2048 GiB}; hqs_tick per tick incl. "
+                                           "D2H of assignments and host-side resource return")
+        extra["drain_m2_cfg3"] = dict(drain(P, make_workload(cfg, seed=0, free_scale=1, variants3=True, blocked_density=0.05), local_rank),
+                                      note="cfg3-M2: as cfg2 with 3 variants per class and 5 % blocked (worker, class, variant) triples")
         t0 = time.perf_counter()
-        left, ticks = N_TASKS, 0
-        while left > 0 and ticks < 5000:
-            m = s2.run_scheduling()
-            if m.n_assigned() == 0:
-                break
-            left -= m.n_assigned()
-            ticks += 1
-            s2.tasks_finished(m.assignments["task"])
-        dt = time.perf_counter() - t0
-        drain = {"value": (N_TASKS - left) / dt, "unit": "assignments/s", "ticks": ticks, "seconds": dt,
-                 "ms_per_tick": 1000.0 * dt / max(ticks, 1), "assigned": N_TASKS - left,
-                 "note": "M2: hqs_tick per tick incl. worker upload, D2H of assignments and host-side resource return"}
-        s2.close()
+        dag = P.make_dag(500_000, 256, N_CLASSES, seed=0)
+        extra["drain_m2_cfg4"] = dict(drain(P, dag, local_rank, dag=True),
+                                      note=f"cfg4-M2: 500k-node DAG (fan-in <= 8, b-level priorities), one tick per completion wave; ticks = waves "
+                                           f"(DAG built on the host in {time.perf_counter() - t0:.1f} s, outside the timed region)")
+        sweep = {}
+        for q in (1, 16, 256, 4096):
+            w2 = make_workload(cfg, seed=0, n_classes=q)
+            res, st2 = device_m1(P, L, w2, 3, local_rank, stream)
+            ms_med = float(np.median([r[0] for r in res]))
+            sweep[f"Q={q}"] = {"kernel_ms": ms_med, "value": res[0][1] / (ms_med / 1e3), "assigned": res[0][1], "classes": len(w2.classes),
+                               "groups": st2["n_groups"], "levels": st2["n_levels"], "coarsened": st2["coarsened"]}
+        extra["class_pool_sweep_m1"] = dict(sweep, note="one context, kernel time by CUDA events (warm task table); Q > 512 exceeds "
+                                                        "HQS_MAX_GROUPS / 8 levels, so the priority levels are coarsened (stat `coarsened`)")
+        seeds = {}
+        for sd in (0, 1, 2):
+            res, _ = device_m1(P, L, make_workload(cfg, seed=sd), 3, local_rank, stream)
+            seeds[str(sd)] = float(np.median([r[1] / (r[0] / 1e3) for r in res]))
+        extra["seeds_m1"] = {"per_seed_value": seeds, "median": float(np.median(list(seeds.values()))),
+                             "note": "cfg2-M1 with seeds 0/1/2, one context each (warm table), assignments/s by kernel time"}
 
     # ---- e2e: host buffers through the public C ABI -----------------------------------------------
     #      every step: this rank's tasks host -> device (hqs_ready_push), the tick, its assignments device -> host
-    e2e = None
-    if world == 1 or p2p:
-        s = scheds[0]
-        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-        h_handles, h_cls, h_prio = pin(handles), pin(np.ascontiguousarray(wl.task_class)), pin(prio)
-        out = torch.empty(N_TASKS * 8, dtype=torch.uint8).pin_memory().numpy().view(L.assignment_dtype)
-        free_after = np.zeros_like(free)
-        n_e2e = max(3, min(K, 10))
+    s = scheds[0]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_handles, h_cls, h_prio = pin(task_handles), pin(wl.task_class), pin(prio)
+    out = torch.empty(n_tasks * 8, dtype=torch.uint8).pin_memory().numpy().view(L.assignment_dtype)
+    free_after = np.zeros_like(free)
+    n_e2e = max(3, min(K, 10))
 
-        def e2e_step():
-            s._check(lib.hqs_ready_push(s._ctx, N_TASKS, L.ptr(h_handles), L.ptr(h_cls), L.ptr(h_prio)))
-            if world == 1:
-                s._check(lib.hqs_tick(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS,
-                                      L.ptr(out), C.byref(out_n), L.ptr(free_after)))
-                assert out_n.value == N_TASKS
+    def e2e_step():
+        s._check(lib.hqs_ready_push(s._ctx, n_tasks, L.ptr(h_handles), L.ptr(h_cls), L.ptr(h_prio)))
+        if world == 1:
+            s._check(lib.hqs_tick(s._ctx, n_workers, L.ptr(workers), L.ptr(free), L.ptr(total), None, n_tasks,
+                                  L.ptr(out), C.byref(out_n), L.ptr(free_after)))
+            assert out_n.value == n_tasks
+        else:
+            if p2p:
+                s._check(lib.hqs_shard_tick_launch(s._ctx, n_workers, L.ptr(workers), L.ptr(free), L.ptr(total), None, n_tasks))
             else:
-                s._check(lib.hqs_shard_tick_launch(s._ctx, N_WORKERS, L.ptr(workers), L.ptr(free), L.ptr(total), None, N_TASKS))
-                s._check(lib.hqs_tick_fetch(s._ctx, N_TASKS, L.ptr(out), C.byref(out_n), L.ptr(free_after)))
-        for _ in range(3):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        n_step = N_TASKS
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            nn = torch.tensor([int(out_n.value)], dtype=torch.int64, device=dev)
-            dist.all_reduce(nn)
-            n_step = int(nn.item())
-        e2e = {"value": n_step / dt, "unit": "assignments/s", "ms_per_step": dt * 1000.0, "steps": n_e2e,
-               "h2d_bytes_per_step": int(world * (N_TASKS * 16 + free.nbytes + total.nbytes + workers.nbytes)),
-               "d2h_bytes_per_step": int(n_step * 8 + world * (free.nbytes + 16)), "n_gpus": world,
-               "note": "per rank: hqs_ready_push + tick + fetch with pinned host buffers; host clock between barriers, max over ranks"}
+                sharded_tick(s, bufs)
+            s._check(lib.hqs_tick_fetch(s._ctx, n_tasks, L.ptr(out), C.byref(out_n), L.ptr(free_after)))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / n_e2e
+    n_step = n_tasks
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        nn = torch.tensor([int(out_n.value)], dtype=torch.int64, device=dev)
+        dist.all_reduce(nn)
+        n_step = int(nn.item())
+    e2e = {"value": n_step / dt, "unit": "assignments/s", "ms_per_step": dt * 1000.0, "steps": n_e2e,
+           "h2d_bytes_per_step": int(world * (n_tasks * 16 + free.nbytes + total.nbytes + workers.nbytes)),
+           "d2h_bytes_per_step": int(n_step * 8 + world * (free.nbytes + 16)), "n_gpus": world,
+           "note": "per rank: hqs_ready_push + tick + fetch with pinned host buffers; host clock between barriers, max over ranks"}
     clocks = sampler.stop()
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample --------------------------
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the same workload ---------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n, dt = oracle_step(args.ref_sample, 0)
-        cpu = {"value": n / dt, "unit": "assignments/s", "cores": 1, "kind": "port",
-               "sample": f"one M1 tick of the restated reference (Python + HiGHS 1.12.0) on a {args.ref_sample}-task cut "
-                         f"of the workload, {dt:.1f} s; host has {os.cpu_count()} cores, 1 used"}
+        n, dtc, cap = oracle_step(cfg, 0)
+        cpu = {"value": n / dtc, "unit": "assignments/s", "cores": 1, "kind": "port",
+               "sample": f"one M1 tick of the restated reference (Python + HiGHS 1.12.0, 1 % MIP gap, 2 s cap{' reached' if cap else ' not reached'}) on the "
+                         f"full workload ({n_tasks} tasks, {n_workers} workers): {n} assignments (the reference assigns at most 1024 tasks of "
+                         f"a class per worker and tick) in {dtc:.1f} s; host has {os.cpu_count()} cores, 1 used"}
 
+    result = None
     if rank == 0:
-        print(json.dumps({
+        result = {
             "metric": METRIC, "value": value, "unit": "assignments/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tasks_per_gpu": N_TASKS, "pool_free_scale": FREE_SCALE * world, "all_assigned": bool(n_per_step == world * N_TASKS), "exchange": ("p2p" if p2p else ("nccl" if world > 1 else "none")), "l2_policy": "each timed step runs on a different "
-                       "12 MB task table (K+W tables, 21 x 12 MB > 126 MB L2): inputs larger than L2",
-                       "host_wall_ms_per_step": 1000.0 * t_host / K},
+            "config": config_block(cfg, world, all_assigned=bool(n_per_step == world * n_tasks),
+                                   exchange=("p2p" if p2p else ("nccl" if world > 1 else "none")),
+                                   l2_policy=f"each timed step runs on a different task table (K+W tables x {12 * n_tasks // 1_000_000} MB "
+                                             "> 126 MB L2): inputs larger than L2",
+                                   host_wall_ms_per_step=1000.0 * t_host / K),
             "gpu_launches": launches_timed, "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "drain_m2": drain,
-        }))
+            "cpu_baseline": cpu, "extra": extra,
+        }
     for s in scheds:
         s.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    return result
 
 
 def main() -> None:
@@ -434,17 +508,37 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-drain", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: wall-clock budget; after it (and at least 3 steps) no further step is started")
+    ap.add_argument("--no-extras", action="store_true", help="skip the M2 drains, the class-pool sweep and the seed sweep")
+    ap.add_argument("--no-drain", action="store_true", help="alias of --no-extras")
     ap.add_argument("--nccl-exchange", action="store_true",
                     help="N > 1: all-gather the count vectors with NCCL instead of the fused peer-to-peer exchange")
     args = ap.parse_args()
+    args.no_extras = args.no_extras or args.no_drain
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_cuda(args)
+    rank = int(os.environ.get("RANK", "0"))
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            res = run_cuda(args)
+            if res is not None:
+                print(json.dumps(res))
+    except BaseException as e:          # every rank reports its own failure; rank 0 still prints one JSON line
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        tb = traceback.format_exc()
+        sys.stderr.write(tb)
+        msg = f"{type(e).__name__}: {e}"
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "impl": args.impl, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                              "value": None, "error": msg, "traceback_tail": tb.strip().splitlines()[-6:]}))
+        sys.stdout.flush()
+        sys.stderr.write(f"[bench] rank {rank} failed: {msg}\n")
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

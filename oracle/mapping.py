@@ -52,6 +52,35 @@ def create_task_mapping(core, solution: SchedulingSolution) -> WorkerTaskMapping
             continue
         idx = 0
         done = False
+        if all(core.tasks[t].state == "waiting" for t in tasks):
+            # Every task goes Waiting -> Assigned (mapping.rs:55-66): the round-robin below is then a pure assignment
+            # of task ids to workers, and k insert_sn_task calls on one worker equal one remove_multiple(rq, k)
+            # (workerload.rs:167-178: k saturating subtractions == one by k * amount).  Same result, without a Python
+            # call per task and resource entry — the benchmark's reference arm runs this on 1 M tasks per tick.
+            per_worker = {w_id: [] for w_id in counts}
+            while not done:
+                for w_id in counts:
+                    if counts[w_id] <= 0:
+                        continue
+                    counts[w_id] -= 1
+                    per_worker[w_id].append(tasks[idx])
+                    idx += 1
+                    if idx >= len(tasks):
+                        done = True
+                        break
+            for w_id, tids in per_worker.items():
+                if not tids:
+                    continue
+                worker = core.workers[w_id]
+                worker.free.remove_multiple(rq, len(tids))
+                assert worker.assigned_tasks.isdisjoint(tids)
+                worker.assigned_tasks.update(tids)
+                up = mapping.update(w_id).assigned
+                for task_id in tids:
+                    task = core.tasks[task_id]
+                    task.state, task.worker, task.rv = "assigned", w_id, v_id
+                    up.append((task_id, v_id))
+            continue
         while not done:
             for w_id in counts:
                 if counts[w_id] <= 0:

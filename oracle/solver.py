@@ -198,6 +198,7 @@ def run_scheduling_solver(core, now: float, batches: Sequence[TaskBatch],
     result.n_vars = len(lp.obj)
     result.n_rows = len(lp.row_lo)
     sol = lp.solve(time_limit=time_limit, mip_rel_gap=mip_rel_gap, accept_incumbent=accept_incumbent)
+    core.last_solver_info = {"hit_time_limit": getattr(lp, "last_status", 0) == 1, "variables": len(lp.obj), "rows": len(lp.row_lo)}
     if sol is None:
         result.solved = False        # non-optimal => empty solution, nothing scheduled (solver.rs:412-415)
         return result
