@@ -332,6 +332,8 @@ def run_cuda(args) -> dict:
     t_host = time.perf_counter() - t_host0
     ms_total = ev0.elapsed_time(ev1)
     launches_timed = K if (world == 1 or p2p) else 2 * K            # tick_k per step (NCCL variant: count_only_k + tick_k)
+    for i in range(Wm):                 # the warm-up ticks are fetched too (a context takes one tick at a time)
+        scheds[i]._check(lib.hqs_tick_fetch(scheds[i]._ctx, n_tasks, L.ptr(tmp_out), C.byref(out_n), None))
     # every step must have assigned every task of the rank
     n_done_local = 0
     for i in range(K):
