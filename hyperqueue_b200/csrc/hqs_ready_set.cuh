@@ -92,7 +92,17 @@ __global__ void remove_k(u32 n, const u32* __restrict__ task, u32* __restrict__ 
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 h = task[i];
-    if (h < n_handles) key[h] &= ~KEY_READY;
+    // the task leaves the table: not ready, and it no longer pins its priority level (level_live_k)
+    if (h < n_handles) key[h] &= ~(KEY_READY | KEY_VALID | KEY_DONE);
+}
+
+// marks the (exact) priority levels that still have a task in the table
+__global__ void level_live_k(u32 n_handles, const u32* __restrict__ key, const u64* __restrict__ prio,
+                             const u64* __restrict__ levels, u32 n_levels, u32* __restrict__ live) {
+    const u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_handles || !(key[h] & KEY_VALID)) return;
+    const u32 lvl = find_level(levels, n_levels, prio[h], false);
+    if (lvl != ~0u && !live[lvl]) live[lvl] = 1u;
 }
 
 __global__ void rearm_k(u32 n_handles, u32* __restrict__ key) {
@@ -124,11 +134,12 @@ __global__ void finished_k(u32 n, const u32* __restrict__ task, const u32* __res
         u32 lo = cons_off[t], hi = cons_off[t + 1];
         for (u32 e = lo; e < hi; ++e) {
             u32 c = cons[e];
-            if (atomicSub(&deps[c], 1u) == 1u) {  // decrease_unfinished_deps() hit zero
+            if (atomicSub(&deps[c], 1u) == 1u && (key[c] & KEY_VALID)) {  // decrease_unfinished_deps() hit zero (a removed consumer stays out)
                 atomicOr(&key[c], KEY_READY);
                 ++made;
             }
         }
+        key[t] &= ~(KEY_VALID | KEY_DONE | KEY_READY);      // finished for good: the handle no longer pins its priority level
     }
     made = __reduce_add_sync(0xffffffffu, made);
     if ((threadIdx.x & 31) == 0 && made) atomicAdd(n_new, made);

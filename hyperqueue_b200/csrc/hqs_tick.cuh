@@ -42,7 +42,7 @@ struct TickSync {
 
 // offsets into the solver CTA's dynamic shared memory (SM_NONE: the array stays in global memory)
 struct TickSmem {
-    u32 fr, rem, unt, remtime, excl, td, frontier, glist, gcl;     // always staged
+    u32 fr, rem, unt, remtime, excl, touch, td, frontier, noresv, glist, gcl;     // always staged
     u32 classes, vorder, blocked, bef, loc;                        // optional
 };
 
@@ -411,7 +411,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     __shared__ u32 s_wcnt[TICK_WARPS];
     __shared__ u32 s_pkpos[PACK_MAX_CAND], s_pknseg[PACK_MAX_CAND], s_pkseglo[PACK_MAX_CAND], s_pkex[PACK_MAX_CAND], s_cbase[PACK_MAX_CAND + 1];
     __shared__ u32 s_blk[8];            // block command: type, li, lj, seg region base, phi (2 words), n_packs
-    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks;
+    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks, s_partial;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 W = a.W, Q = a.Q, R = a.R, G = a.G;
     const u32 nW = gridDim.x - 1;
@@ -423,7 +423,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     AT* s_fr = reinterpret_cast<AT*>(smem + a.sm.fr);                                  // [W][RT]
     u32* s_unt = reinterpret_cast<u32*>(smem + a.sm.unt);                              // [W] bit r: free == total != 0
     u64* s_remtime = reinterpret_cast<u64*>(smem + a.sm.remtime);                      // [W]
-    uint8_t* s_excl = smem + a.sm.excl;                                                // [W]
+    uint8_t* s_excl = smem + a.sm.excl;                                                // [W] 1: minimum utilisation, 2: reserved
+    uint8_t* s_touch = smem + a.sm.touch;                                              // [W] the worker received something in this tick
+    uint8_t* s_noresv = smem + a.sm.noresv;                                            // [Q] no worker can be reserved for the class any more
     unsigned short* s_td = reinterpret_cast<unsigned short*>(smem + a.sm.td);          // [W] tried | dead << 8 of the current group
     unsigned short* s_front = reinterpret_cast<unsigned short*>(smem + a.sm.frontier); // [Q] first tile that may have room
     uint2* s_glist = reinterpret_cast<uint2*>(smem + a.sm.glist);                      // [L*Q] (group, count)
@@ -461,8 +463,10 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     s_fr[(size_t)w * RT + r] = n;
                 }
                 unt |= (t != 0 && n == t) ? (1u << r) : 0u;
+                if (n != t) s_partial = 1;          // partly occupied at tick start: reservations are possible
             }
             s_unt[w] = unt;
+            s_touch[w] = 0;
         }
     };
     // s_C[r] = sum over workers of the exact free amount, saturating (MAX absorbs); warp r handles resource r (+16 ...)
@@ -477,7 +481,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     };
 
     // ---- prologue A: staging (overlaps the histogram of the worker CTAs)
-    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; }
+    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; s_partial = 0; }
     if (tid < HQS_MAX_RESOURCES) { s_totmax[tid] = 0; s_D[tid] = 0; s_C[tid] = 0; }
     if (a.sm.classes != SM_NONE) {
         const uint4* src = reinterpret_cast<const uint4*>(a.classes);
@@ -501,7 +505,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         s_excl[w] = 0;
         if (a.min_util) a.excl_glob[w] = 0;
     }
-    for (u32 c = tid; c < Q; c += blockDim.x) s_front[c] = 0;
+    for (u32 c = tid; c < Q; c += blockDim.x) { s_front[c] = 0; s_noresv[c] = 0; }
     __syncthreads();
     stage_workers();
     // per-resource maximum of the (scaled) worker totals: a class no worker is big enough for is not demand
@@ -664,7 +668,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         if (cmd == BLK_RESTART) {
             // min-utilisation restart: excluded workers stay out, everything else starts over
             stage_workers();
-            for (u32 c = tid; c < Q; c += blockDim.x) s_front[c] = 0;
+            for (u32 c = tid; c < Q; c += blockDim.x) { s_front[c] = 0; s_noresv[c] = 0; }
+            for (u32 w = tid; w < W; w += blockDim.x)
+                if (s_excl[w] == 2) s_excl[w] = 0;         // reservations are made again by the new pass
             bar_named(2, TICK_THREADS);
             return;
         }
@@ -790,6 +796,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         for (int r = 0; r < RT; ++r)
                             if (((dv.used_mask >> r) & 1) && s_fr[(size_t)w * RT + r] != AMAX) touched |= 1u << r;
                         atomicAnd(&s_unt[w], ~touched);
+                        s_touch[w] = 1;
                     }
                     if (k) *tk = k - use;
                     if (__ballot_sync(0xffffffffu, k > use)) { ex_lo = ex_lo < tile ? ex_lo : tile; ex_hi = ex_hi > tile + 1 ? ex_hi : tile + 1; }
@@ -802,6 +809,80 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         }
         __threadfence();
         bar_named(2, TICK_THREADS);
+    };
+
+    // ---- reservations (solver.rs:133-151; specification: tests/greedy_model.py::_Tick.reserve).  A class that is left
+    //      with unplaced tasks claims workers that are big enough for it by their TOTALS but cannot take one task of it at
+    //      tick start: such a worker receives nothing in this tick.  Only workers without any assignment in this tick, at
+    //      most one per unplaced task, highest worker index first, and only while the class's count does not exceed the
+    //      batch limit (every capable worker counts at least once, batches.rs:80-91).  Rare path: exact 64-bit arithmetic
+    //      on the tick input.
+    const ClassT<RT, u64>* classes64 = reinterpret_cast<const ClassT<RT, u64>*>(a.classes64);
+    auto reserve_for = [&](u32 c, u32 n_all, u32 remaining) {
+        const ClassT<RT, u64>& cl = classes64[c];
+        const u32 nv = cl.n_variants;
+        u64 limit = 0;
+        // per lane and tile: capable by totals?  how many fit at tick start (sum over variants, 1024 each)?
+        for (u32 tile = 0; tile < n_tiles; ++tile) {
+            const u32 w = tile * 32 + lane;
+            u64 lim_w = 0;
+            if (w < W) {
+                const u64 rt = s_remtime[w];
+                bool cap = false;
+                u64 fits = 0;
+                for (u32 v = 0; v < nv; ++v) {
+                    const VarT<RT, u64>& dv = cl.v[v];
+                    bool ok = rt == HQS_TIME_INF || dv.min_time_ms <= rt;
+                    u64 cnt = HQS_AMOUNT_MAX;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        if (r >= (int)R || !((dv.used_mask >> r) & 1)) continue;
+                        const u64 t = a.total_rw[(size_t)w * R + r], f = a.free_rw[(size_t)w * R + r];
+                        if ((dv.all_mask >> r) & 1) { ok &= t != 0; cnt = cnt < (f != 0 ? 1ull : 0ull) ? cnt : (f != 0 ? 1ull : 0ull); }
+                        else { ok &= dv.amount[r] <= t; if (f != HQS_AMOUNT_MAX) { const u64 q = f / dv.amount[r]; cnt = cnt < q ? cnt : q; } }
+                    }
+                    cap |= ok;
+                    fits += cnt < 1024 ? cnt : 1024;
+                }
+                if (cap) lim_w = fits > 1 ? fits : 1;
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) lim_w += __shfl_xor_sync(0xffffffffu, lim_w, d);
+            limit += lim_w;
+        }
+        u32 got = 0;
+        if ((u64)n_all <= limit) {
+            for (u32 tile = n_tiles; tile-- > 0 && got < remaining;) {
+                const u32 w = tile * 32 + lane;
+                bool elig = false;
+                if (w < W && !s_excl[w] && !s_touch[w]) {
+                    const u64 rt = s_remtime[w];
+                    bool cap = false, fits_now = false;
+                    for (u32 v = 0; v < nv; ++v) {
+                        const VarT<RT, u64>& dv = cl.v[v];
+                        bool ok = rt == HQS_TIME_INF || dv.min_time_ms <= rt;
+                        bool one = true;
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            if (r >= (int)R || !((dv.used_mask >> r) & 1)) continue;
+                            const u64 t = a.total_rw[(size_t)w * R + r], f = a.free_rw[(size_t)w * R + r];
+                            if ((dv.all_mask >> r) & 1) { ok &= t != 0; one &= f != 0; }
+                            else { ok &= dv.amount[r] <= t; one &= f == HQS_AMOUNT_MAX || dv.amount[r] <= f; }
+                        }
+                        cap |= ok;
+                        fits_now |= one;
+                    }
+                    elig = cap && !fits_now;
+                }
+                const u32 em = __ballot_sync(0xffffffffu, elig);
+                // the highest (remaining - got) eligible lanes of the tile
+                const u32 above = __popc(em & ~((2u << lane) - 1u));          // eligible lanes with a higher index
+                if (elig && above < remaining - got) s_excl[w] = 2;
+                got += min((u32)__popc(em), remaining - got);
+            }
+        }
+        if (got < remaining && lane == 0) s_noresv[c] = 1;    // eligibility only shrinks during a tick
+        __syncwarp();
     };
 
     // =============================================================================================
@@ -911,7 +992,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     //      vectors stay in registers (lane = worker) from group to group, the next group's request is
                     //      prefetched, and the only work on the group-to-group dependency chain is fit -> ballot -> take.
                     u32 cur_tile = 0xFFFFFFFFu;
-                    bool dirty = false;
+                    bool dirty = false, lane_excl = false;
                     AT fr[RT];
 #pragma unroll
                     for (int r = 0; r < RT; ++r) fr[r] = 0;
@@ -948,11 +1029,12 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 }
 #pragma unroll
                                 for (int r = 0; r < RT; ++r) fr[r] = w < W ? s_fr[(size_t)w * RT + r] : 0;
+                                lane_excl = w < W && s_excl[w] != 0;              // reserved for a waiting class
                                 cur_tile = tile;
                                 dirty = false;
                             }
                             ++n_visits;
-                            const u64 cnt = fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
+                            const u64 cnt = lane_excl ? 0 : fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
                             const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
                             u32 take = 0, exc = 0, handed = 0;
                             if (hasm) {
@@ -992,6 +1074,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w; }
                             }
                             take_from<RT, AT>(fr, dv, take);                       // take == 0 leaves the lane as it is
+                            if (take) s_touch[w] = 1;
                             dirty |= tkm != 0;
                             seg_cur += __popc(tkm);
                             if (front) {
@@ -1003,6 +1086,21 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         }
                         if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
                         if (c_n == c) front_n = f;                               // the same class again (next level)
+                        if (remaining && s_partial && !s_noresv[c]) {
+                            // the class is left with unplaced tasks: reservations.  The tile in registers goes back first
+                            // and is loaded again afterwards (with the new exclusions)
+                            if (dirty) {
+                                const u32 wo = cur_tile * 32 + lane;
+                                if (wo < W) {
+#pragma unroll
+                                    for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
+                                }
+                                dirty = false;
+                            }
+                            __syncwarp();
+                            reserve_for(c, n_all, remaining);
+                            cur_tile = 0xFFFFFFFFu;
+                        }
                         const u32 k = n_all - remaining;
                         u32 k_loc = k;
                         if (before) {
@@ -1167,6 +1265,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 for (int r = 0; r < RT; ++r)
                                     if (((dv.used_mask >> r) & 1) && !((dv.all_mask >> r) & 1) && fr[r] != AMAX) touched |= 1u << r;
                                 s_unt[w] = unt & ~touched;
+                                s_touch[w] = 1;
                                 if constexpr (NARROW) {
                                     // `All` consumed the whole resource: the exact free amount is 0, remainder included
                                     const u32 z = dv.all_mask & dv.used_mask;
@@ -1198,6 +1297,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             __syncwarp();
                         }
                     }
+                    if (remaining && s_partial && !s_noresv[c]) reserve_for(c, n_all, remaining);
                     const u32 k = n_all - remaining;
                     // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
                     u32 k_loc = k;

@@ -91,6 +91,8 @@ struct hqs_ctx {
     std::vector<u64> levels;      // exact distinct priorities seen, descending
     std::vector<u64> dev_levels;  // what the device uses (== levels, or bucket bounds when coarsened)
     bool coarse = false;
+    bool levels_declared = false;   // hqs_levels_add was used: the caller numbers the levels (sharded ready set), no pruning
+    size_t levels_pruned_at = 0;    // size of the level set after the last pruning
     u64* d_levels = nullptr;
     u32 d_levels_cap = 0;
     // task table
@@ -228,6 +230,43 @@ int relevel_all(hqs_ctx* ctx) {
     ctx->stats.kernel_launches++;
     CU(cudaGetLastError());
     return HQS_OK;
+}
+
+// Drops the priority levels no task of the table carries any more (tako priorities have a per-job component, so a
+// long-running server sees one level per job ever submitted).  Called when the level set is about to exceed what the
+// group limit allows, or has doubled since the last pruning.  Returns true if levels were dropped (the caller then
+// uploads the table and re-keys the tasks).
+int prune_levels(hqs_ctx* ctx, bool* changed) {
+    *changed = false;
+    const u32 L = (u32)ctx->levels.size();
+    if (ctx->levels_declared || L == 0 || ctx->n_handles == 0) return HQS_OK;
+    u64* d_lv = nullptr;
+    u32* d_live = nullptr;
+    CU(cudaMalloc(&d_lv, (size_t)L * 8));
+    CU(cudaMalloc(&d_live, (size_t)L * 4));
+    CU(cudaMemsetAsync(d_live, 0, (size_t)L * 4, ctx->stream));
+    CU(cudaMemcpyAsync(d_lv, ctx->levels.data(), (size_t)L * 8, cudaMemcpyHostToDevice, ctx->stream));
+    level_live_k<<<(ctx->n_handles + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_handles, ctx->d_key, ctx->d_prio, d_lv, L, d_live);
+    ctx->stats.kernel_launches++;
+    std::vector<u32> live(L);
+    CU(cudaMemcpyAsync(live.data(), d_live, (size_t)L * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(d_lv));
+    CU(cudaFree(d_live));
+    std::vector<u64> kept;
+    kept.reserve(L);
+    for (u32 i = 0; i < L; ++i)
+        if (live[i]) kept.push_back(ctx->levels[i]);
+    *changed = kept.size() != ctx->levels.size();
+    ctx->levels.swap(kept);
+    ctx->levels_pruned_at = ctx->levels.size();
+    return HQS_OK;
+}
+
+// the level set outgrew the group budget, or doubled since it was last pruned
+bool levels_need_pruning(const hqs_ctx* ctx) {
+    const size_t max_levels = std::max<u32>(1, HQS_MAX_GROUPS / std::max<u32>(ctx->Q, 1));
+    return !ctx->levels_declared && (ctx->levels.size() > max_levels || ctx->levels.size() > 2 * ctx->levels_pruned_at + 64);
 }
 
 // merges new distinct priorities into the level set; returns true if the set changed
@@ -561,8 +600,10 @@ size_t solver_layout(const hqs_ctx* ctx, TickArgs& a, size_t budget, bool sharde
     a.sm.unt = put((size_t)W * 4);
     a.sm.remtime = put((size_t)W * 8);
     a.sm.excl = put(W);
+    a.sm.touch = put(W);
     a.sm.td = put((size_t)W * 2);
     a.sm.frontier = put((size_t)Q * 2);
+    a.sm.noresv = put(Q);
     a.sm.glist = put((size_t)n_pos * 8);
     a.sm.gcl = put((size_t)n_pos * 4);
     auto opt = [&](size_t bytes, bool wanted) -> u32 {
@@ -844,9 +885,11 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
         // the level budget depends on Q: re-derive (possibly coarsened) levels and re-key the table
         const bool was_coarse = ctx->coarse;
         const size_t old_n = ctx->dev_levels.size();
-        int rc = upload_levels(ctx);
-        if (rc) return rc;
-        if (was_coarse || ctx->coarse || old_n != ctx->dev_levels.size())
+        bool dropped = false;
+        int rc = HQS_OK;
+        if (levels_need_pruning(ctx) && (rc = prune_levels(ctx, &dropped))) return rc;
+        if ((rc = upload_levels(ctx))) return rc;
+        if (dropped || was_coarse || ctx->coarse || old_n != ctx->dev_levels.size())
             if ((rc = relevel_all(ctx))) return rc;
     }
     return HQS_OK;
@@ -901,6 +944,10 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
             distinct_priorities(priority, n, fresh);
         }
         merge_levels(ctx, fresh);
+        if (levels_need_pruning(ctx)) {
+            bool dropped = false;
+            if ((rc = prune_levels(ctx, &dropped))) return rc;
+        }
         if ((rc = upload_levels(ctx))) return rc;
         if ((rc = relevel_all(ctx))) return rc;
     }
@@ -914,6 +961,7 @@ int hqs_levels_add(hqs_ctx* ctx, uint32_t n, const uint64_t* priority) {
     CU(cudaSetDevice(ctx->device));
     std::vector<u64> fresh;
     distinct_priorities(priority, n, fresh);
+    ctx->levels_declared = true;
     if (!merge_levels(ctx, fresh)) return HQS_OK;
     int rc = upload_levels(ctx);
     if (rc) return rc;

@@ -109,8 +109,15 @@ void GpuCore::unblock_request(WorkerId id, ResourceRqId rq, ResourceVariantId v)
     b.erase(std::remove(b.begin(), b.end(), std::make_pair(rq, v)), b.end());
 }
 
-// Dense handles are given out in arrival order.  tako creates the tasks of a job in ascending TaskId, so handle
-// order == TaskId order inside a job, which is the tie-break the device uses inside a (priority, class) group.
+// on_new_tasks (reactor.rs:188-220): the tasks of a submit become known.  Handles are given out here in ascending
+// TaskId — the device pops a (priority, class) group in ascending handle, the reference in ascending TaskId
+// (taskqueue.rs:395-420) — and job ids grow with every submit, so handle order == TaskId order across submits too.
+void GpuCore::on_new_tasks(std::vector<TaskId> tasks) {
+    std::sort(tasks.begin(), tasks.end(), [](const TaskId& a, const TaskId& b) { return a.as_u64() < b.as_u64(); });
+    for (const TaskId& t : tasks) handle_of(t);
+}
+
+// A task that was never announced through on_new_tasks gets its handle on first use (arrival order).
 uint32_t GpuCore::handle_of(TaskId task) {
     auto it = handle_of_.find(task.as_u64());
     if (it != handle_of_.end()) return it->second;
@@ -144,6 +151,14 @@ void GpuCore::remove_ready_task(TaskId task) {
 }
 
 void GpuCore::flush_ready() {
+    if (!forget_h_.empty()) {
+        // finished tasks leave the device table for good, so their handles stop pinning priority levels (the device
+        // prunes levels without tasks: tako priorities carry a per-job component)
+        if (hqs_ready_remove(ctx_, (uint32_t)forget_h_.size(), forget_h_.data()) != HQS_OK) {
+            last_error_ = hqs_last_error(ctx_); log_error("hqs_ready_remove (finished tasks)", last_error_.c_str());
+        }
+        forget_h_.clear();
+    }
     if (push_h_.empty()) return;
     flush_classes();
     const int rc = hqs_ready_push(ctx_, (uint32_t)push_h_.size(), push_h_.data(), push_c_.data(), push_p_.data());
@@ -238,6 +253,7 @@ void GpuCore::on_task_finished(TaskId task) {
     }
     t.worker = -1;
     t.live = false;
+    forget_h_.push_back(it->second);
 }
 
 }  // namespace tako_b200

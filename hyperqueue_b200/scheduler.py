@@ -314,15 +314,25 @@ class GpuScheduler:
             return int(n_new.value)
         return 0
 
-    def new_worker_query(self, worker_totals: np.ndarray, now: float = 0.0):
+    def new_worker_query(self, worker_totals: np.ndarray, now: float = 0.0, remaining_s: Optional[np.ndarray] = None,
+                         min_utilization: Optional[np.ndarray] = None):
         """compute_new_worker_query (scheduler/query.rs:12-131): which of these HYPOTHETICAL workers would get
-        work from the current ready set?  Nothing is consumed.  Returns (needed[bool], counts, total)."""
+        work from the current ready set?  Nothing is consumed.  Partial descriptors use HQS_AMOUNT_MAX for unknown
+        resources (query.rs:35-46); remaining_s = time limits of the allocation (inf = none); min_utilization as in
+        WorkerConfiguration.  Returns (needed[bool], counts, total)."""
         self._sync_classes()
         tot = np.ascontiguousarray(worker_totals, dtype=np.uint64)
         nw = tot.shape[0]
         w = np.zeros(nw, dtype=L.worker_dtype)
         w["worker_id"] = np.arange(nw, dtype=np.uint32)
-        w["remaining_time_ms"] = np.uint64(L.HQS_TIME_INF)
+        rem = np.full(nw, L.HQS_TIME_INF, dtype=np.uint64)
+        if remaining_s is not None:
+            r = np.asarray(remaining_s, dtype=np.float64)
+            finite = ~np.isinf(r)
+            rem[finite] = (np.maximum(r[finite], 0.0) * 1000.0).astype(np.uint64)
+        w["remaining_time_ms"] = rem
+        if min_utilization is not None:
+            w["min_utilization"] = np.asarray(min_utilization, dtype=np.float32)
         counts = np.zeros(nw, dtype=np.uint32)
         n = C.c_uint32(0)
         self._check(self._lib.hqs_query(self._ctx, nw, L.ptr(w), L.ptr(tot), L.ptr(tot), None, C.byref(n), L.ptr(counts), None))

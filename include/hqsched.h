@@ -102,7 +102,8 @@ typedef struct {
     uint64_t kernel_launches;   /* kernels launched by this context so far                        */
     uint64_t ticks;
     uint32_t n_handles;         /* size of the device task table                                  */
-    uint32_t coarsened;         /* 1 if priority levels had to be merged to fit HQS_MAX_GROUPS    */
+    uint32_t coarsened;         /* 1 if LIVE priority levels had to be merged to fit HQS_MAX_GROUPS: tasks of merged
+                                   levels are then ordered by class and handle, not by priority — log it         */
     uint32_t narrow_amounts;    /* 1 if the last tick solved on gcd-scaled 32-bit amounts          */
     uint32_t reserved;
 } hqs_stats;
@@ -131,9 +132,13 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes);
 int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
                    const uint64_t* priority);
 /* Declares priority values before any task carries them.  Needed when the ready set is sharded over
- * several contexts (every rank must number the priority levels identically); harmless otherwise. */
+ * several contexts (every rank must number the priority levels identically).  A context whose levels were declared
+ * does not prune them on its own (the ranks would diverge). */
 int hqs_levels_add(hqs_ctx* ctx, uint32_t n, const uint64_t* priority);
-/* TaskQueue::remove (taskqueue.rs:194-216): cancel / externally assigned tasks leave the ready set. */
+/* TaskQueue::remove (taskqueue.rs:194-216): cancel / externally assigned tasks leave the ready set.  Also the way to
+ * retire the handle of a task that has FINISHED: a removed handle leaves the device table, so it no longer pins its
+ * priority level (levels without any task are pruned when the level set outgrows HQS_MAX_GROUPS / n_classes or doubles;
+ * tako priorities carry a per-job component, so a long-running server would otherwise accumulate one level per job). */
 int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task);
 
 /* DAG mode (reactor.rs:188-220 on_new_tasks + :500-580 task_finished, device resident): loads a whole

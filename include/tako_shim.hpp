@@ -11,6 +11,7 @@
 //   Priority::from_user_priority (priority.rs:43-48)                  priority_from_user
 //   on_new_worker / on_remove_worker (reactor.rs:20-32, 64-186)       GpuCore::on_new_worker / on_remove_worker
 //   Worker::block_request / unblock (worker.rs:328-344)               GpuCore::block_request / unblock_request
+//   on_new_tasks (reactor.rs:188-220)                                 GpuCore::on_new_tasks (handles in TaskId order)
 //   TaskQueues::add_ready_task (taskqueue.rs:37-43)                   GpuCore::add_ready_task
 //   TaskQueue::remove (taskqueue.rs:194-216)                          GpuCore::remove_ready_task
 //   run_scheduling_inner (main.rs:40-46) -> WorkerTaskMapping         GpuCore::run_scheduling
@@ -101,6 +102,8 @@ public:
     void block_request(WorkerId id, ResourceRqId rq, ResourceVariantId v);
     void unblock_request(WorkerId id, ResourceRqId rq, ResourceVariantId v);
 
+    // on_new_tasks (reactor.rs:188-220): announces the tasks of a submit; handles are assigned in ascending TaskId
+    void on_new_tasks(std::vector<TaskId> tasks);
     void add_ready_task(TaskId task, ResourceRqId rq, Priority priority);
     void remove_ready_task(TaskId task);
 
@@ -140,6 +143,7 @@ private:
     std::unordered_map<uint64_t, uint32_t> handle_of_;       // TaskId -> dense handle
     std::vector<TaskState> tasks_;                           // by handle
     std::vector<uint32_t> push_h_, push_c_;
+    std::vector<uint32_t> forget_h_;                         // finished tasks: leave the device table at the next flush
     std::vector<uint64_t> push_p_;
     std::vector<hqs_assignment> out_;
     std::string last_error_;

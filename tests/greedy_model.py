@@ -105,12 +105,64 @@ class _Tick:
         self.wl = wl
         self.W, self.R = free.shape
         self.fr = [[int(x) for x in free[w]] for w in range(self.W)]
+        self.fr0 = [list(x) for x in self.fr]
         self.tot = [[int(x) for x in wl.worker_total[w]] for w in range(self.W)]
         self.rem_ms = [int(x) for x in remaining_ms]
         self.am = [[{r: int(a) for r, a in d["amounts"].items()} for d in vs] for vs in wl.classes]
         self.alls = [[tuple(d.get("all", ())) for d in vs] for vs in wl.classes]
         self.min_ms = [[int(round(d.get("min_time_s", 0.0) * 1000)) for d in vs] for vs in wl.classes]
         self.excluded = None
+        self.touched = [False] * self.W          # the worker received something in this tick
+        self.noresv = set()                      # classes for which no worker can be reserved any more
+
+    def capable(self, w: int, c: int) -> bool:
+        """Worker::is_capable_to_run_rqv (worker.rs:280-299): some variant fits the TOTALS and the remaining time."""
+        tot, rt = self.tot[w], self.rem_ms[w]
+        for v in range(len(self.am[c])):
+            if rt != TIME_INF and self.min_ms[c][v] > rt:
+                continue
+            if all(a <= tot[r] for r, a in self.am[c][v].items()) and all(tot[r] != 0 for r in self.alls[c][v]):
+                return True
+        return False
+
+    def reserve(self, c: int, n_all: int, remaining: int) -> None:
+        """Reservations (solver.rs:133-151): a class that is left with unplaced tasks may claim workers that are big
+        enough for it (by their totals) but cannot take a single task of it right now — such a worker receives nothing
+        in this tick, so that running tasks drain and the waiting class gets in instead of being starved by lower
+        priorities.  As in the reference: only workers without a placement variable for the class (nothing of it fits at
+        tick start) and without any assignment in this tick, at most one per unplaced task, only while the class's count
+        does not exceed the batch limit (batches.rs:80-91: every capable worker counts at least once), and the MILP's
+        preference for HIGH worker indices (coefficient w_idx / (100 n)) is kept."""
+        if c in self.noresv:
+            return
+        cap = [w for w in range(self.W) if self.capable(w, c)]
+        limit = 0
+        for w in cap:
+            limit += max(1, sum(min(self.fit_start(w, c, v), 1024) for v in range(len(self.am[c]))))
+        got = 0
+        if n_all <= limit:
+            for w in reversed(cap):
+                if got >= remaining:
+                    break
+                if (self.excluded is not None and self.excluded[w]) or self.touched[w]:
+                    continue
+                if any(self.fit_start(w, c, v) > 0 for v in range(len(self.am[c]))):
+                    continue
+                self.excluded[w] = True
+                got += 1
+        if got < remaining:
+            self.noresv.add(c)            # eligibility only shrinks during a tick
+
+    def fit_start(self, w: int, c: int, v: int) -> int:
+        """task_max_count of variant v against the free vector at tick start, blocked requests ignored (workerload.rs:121-145)."""
+        fr, tot = self.fr0[w], self.tot[w]
+        cnt = U64
+        for r in range(self.R):
+            if r in self.alls[c][v]:
+                cnt = min(cnt, 1 if fr[r] != 0 else 0)
+            elif r in self.am[c][v] and fr[r] != AMOUNT_MAX:
+                cnt = min(cnt, fr[r] // self.am[c][v][r])
+        return cnt
 
     def admissible(self, w: int, c: int, v: int) -> bool:
         if self.excluded is not None and self.excluded[w]:
@@ -163,6 +215,8 @@ class _Tick:
 
     def take(self, w: int, c: int, v: int, k: int) -> None:
         fr = self.fr[w]
+        if k:
+            self.touched[w] = True
         for r in range(self.R):
             if r in self.alls[c][v]:
                 fr[r] = 0
@@ -328,6 +382,8 @@ def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remai
         remaining_ms = wl.remaining_ms()
     t = _Tick(wl, free, remaining_ms)
     t.excluded = [bool(x) for x in excluded]
+    # reservations can only exist when some worker is partly occupied at tick start (free != total)
+    t.any_partial = any(t.fr0[w][r] != t.tot[w][r] for w in range(W) for r in range(R))
     order = class_order(wl, free, wl.worker_total)
     vorder = variant_order(wl, free)
     out: List[Tuple[int, int, int, int]] = []
@@ -388,6 +444,8 @@ def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remai
                         out.append((tt, w, v, 0))
                     pos += cnt
                     remaining -= cnt
+            if remaining and t.any_partial:
+                t.reserve(c, n, remaining)
     a = np.array(out, dtype=assignment_dtype) if out else np.zeros(0, dtype=assignment_dtype)
     return a, np.array(t.fr, dtype=np.uint64)
 

@@ -85,7 +85,7 @@ def oracle_tick(core: Core, now: float = 0.0, **solver_opts):
     return (np.array(ts, dtype=np.int64), np.array(ws, dtype=np.int64), np.array(vs, dtype=np.int64), mapping)
 
 
-def oracle_drain(wl: Workload, max_ticks: int = 100000, disable_prefill: bool = True):
+def oracle_drain(wl: Workload, max_ticks: int = 100000, disable_prefill: bool = True, solver_opts: Optional[dict] = None):
     """Zero-duration drain (cfg(zero_worker) semantics): tick, every assigned task finishes at once,
     resources return, newly ready consumers enter the queues; repeat.  Returns (ticks, per-tick counts)."""
     core = oracle_core(wl)
@@ -94,7 +94,7 @@ def oracle_drain(wl: Workload, max_ticks: int = 100000, disable_prefill: bool = 
     remaining = wl.n_tasks
     per_tick = []
     while remaining > 0 and len(per_tick) < max_ticks:
-        ts, ws, vs, _ = oracle_tick(core)
+        ts, ws, vs, _ = oracle_tick(core, **(solver_opts or {}))
         if ts.size == 0:
             raise RuntimeError(f"oracle drain stalled with {remaining} tasks left")
         for t, w in zip(ts.tolist(), ws.tolist()):

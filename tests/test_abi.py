@@ -108,7 +108,7 @@ def test_solver_shared_memory_budget(lib):
     statics = [int(m) for blk in re.findall(r"Function [^\n]*tick_k[^\n]*\n[^\n]*", out) for m in re.findall(r"SHARED:(\d+)", blk)]
     assert len(statics) == 6
     W, Q, n_pos = 1024, 4096, 4096
-    worst_mandatory = W * 16 * 8 + W * (4 + 8 + 1 + 2) + Q * 2 + n_pos * 12 + 8 * 16
+    worst_mandatory = W * 16 * 8 + W * (4 + 8 + 1 + 1 + 2) + Q * 3 + n_pos * 12 + 10 * 16
     assert max(statics) + worst_mandatory <= 227 * 1024, (max(statics), worst_mandatory)
     # the emit step of the worker CTAs: <= 128 KB of counters + 64 KB of group records + the segment cache
     assert max(statics) + 128 * 1024 + 64 * 1024 + 8 * 1024 <= 227 * 1024

@@ -214,6 +214,53 @@ def test_too_small_out_cap_fails_before_anything_is_consumed():
     s.close()
 
 
+def test_priority_levels_of_departed_tasks_are_pruned():
+    """tako priorities carry a per-job component, so a long-running server sees ever new priority values.  Levels that no
+    task of the table carries any more are dropped before the level set would have to be coarsened: after 6 waves of
+    1500 distinct priorities each (9000 values, far beyond HQS_MAX_GROUPS / 2 classes = 2048 levels) the ticks are still
+    exact (priority order is kept), because at most one wave is alive at a time."""
+    from hyperqueue_b200 import GpuScheduler, RequestVariant, priority_from_user
+    s = GpuScheduler(1)
+    c1 = s.get_or_create_resource_rq_id([RequestVariant.of({0: 1 * FR})])
+    c2 = s.get_or_create_resource_rq_id([RequestVariant.of({0: 2 * FR})])
+    s.new_worker(1, [64 * FR])
+    n = 1500
+    for wave in range(6):
+        h = np.arange(n, dtype=np.uint32)
+        up = (wave * n + np.arange(n)).astype(np.int64)                 # 1500 fresh priority values per wave
+        cls = np.where(np.arange(n) % 2 == 0, c1, c2).astype(np.uint32)
+        s.add_ready_tasks(h, cls, priority_from_user(up))
+        st = s.stats()
+        assert st["coarsened"] == 0 and st["n_levels"] <= 2 * n + 64, (wave, st)
+        m = s.run_scheduling()
+        a = m.assignments
+        # 64 cpus: the highest priorities first, strictly by priority
+        assert a.shape[0] > 0 and (np.diff(up[a["task"]]) < 0).all()
+        assert up[a["task"]].min() >= n * wave + n - 64
+        s.tasks_finished(a["task"])
+        s.remove_ready_tasks(h)                                         # the wave leaves (finished or cancelled)
+    s.close()
+
+
+def test_1024_worker_pool_tick_cfg5_shape():
+    """BASELINE configs[4] pool: 1024 workers (32 worker tiles).  Small task count against the specification bit for bit,
+    then the per-GPU share of cfg5 (1.25 M tasks, capacity >= demand) through the judge and the exact replay."""
+    wl = P.make_independent(30000, 1024, 16, seed=11)
+    _check_exact(wl)
+    wl = P.make_independent(1_250_000, 1024, 16, seed=12, free_scale=1024)
+    s = P.gpu_scheduler(wl)
+    fb = s.free.copy()
+    m = s.run_scheduling()
+    a = m.assignments
+    assert a.shape[0] == wl.n_tasks and np.array_equal(np.sort(a["task"]), np.arange(wl.n_tasks, dtype=np.uint32))
+    assert P.judge_tick(wl, fb, a).ok
+    amounts, allm, _, _ = wl.class_tables()
+    from oracle import judge as J
+    assert np.array_equal(J.replay_free_after(amounts, allm, fb, wl.worker_total, wl.task_class, a["task"], a["worker"], a["variant"]), m.free_after)
+    assert (np.diff(wl.task_user_priority[a["task"]]) <= 0).all()
+    s.close()
+
+
 def test_new_worker_query_is_a_dry_run():
     """Shape of test_query.rs: fake workers, partial descriptors with MAX, nothing consumed."""
     wl = P.make_independent(3000, 4, 4, seed=12)

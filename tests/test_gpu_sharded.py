@@ -79,7 +79,7 @@ def test_two_shards_on_one_gpu_equal_single_context(n, w, q, scale):
     assert np.array_equal(got, exp)
 
 
-@pytest.mark.parametrize("n,w,q,scale", [(30000, 16, 8, 1), (100001, 64, 16, 1024)])
+@pytest.mark.parametrize("n,w,q,scale", [(30000, 16, 8, 1), (100001, 64, 16, 1024), (200000, 1024, 16, 1024), (60000, 1024, 16, 1)])
 def test_two_shards_peer_exchange_on_one_gpu(n, w, q, scale):
     """The fused sharded tick (count -> peer stores + release flag -> solver acquires and sums -> emit) with two
     contexts of ONE process attached to each other's exchange buffers; three ticks in a row exercise the

@@ -1,8 +1,10 @@
-"""The autoalloc what-if query (scheduler/query.rs) answered by the DEVICE algorithm's sequential specification
-(tests/greedy_model.py == the CUDA path bit for bit, here what `hqs_query` computes over hypothetical workers):
-the reference's tests/test_query.rs cases, with the ready set produced by the oracle's own tick.  The reference asks
-"which of these fake workers would receive at least one task"; the greedy reaches the reference's answer on every
-single-node case without `min_utilization`, and with it through the shim's post-filter rule."""
+"""The autoalloc what-if query (scheduler/query.rs) answered by the DEVICE algorithm: the reference's tests/test_query.rs
+cases, with the ready set produced by the oracle's own tick.  The reference asks "which of these fake workers would
+receive at least one task".  Two backends run the same cases:
+  spec  tests/greedy_model.py, the sequential specification (CPU; this module's own tests)
+  gpu   hqs_query through GpuScheduler.new_worker_query (tests/test_gpu_query.py re-runs every test of this module on the
+        device and additionally requires the per-worker counts to equal the specification's)
+min_utilization (query.rs:35-46 -> solver.rs:479-518) is part of the tick in both."""
 import numpy as np
 import pytest
 
@@ -11,9 +13,12 @@ from oracle.model import AMOUNT_MAX, units
 from oracle_env import TaskBuilder, TestEnv, WorkerBuilder
 from workloads import Workload
 
+_BACKEND = "spec"
 
-def spec_query(rt, queries):
-    """queries: [(resources [(name, units)], partial, time_limit_s, max_sn_workers, min_utilization)]"""
+
+def query_workload(rt, queries):
+    """queries: [(resources [(name, units)], partial, time_limit_s, max_sn_workers, min_utilization)] ->
+    (Workload over the ready set with the fake workers as its pool, min_utilization per worker, owner query per worker)"""
     core = rt.core
     for res, *_ in queries:
         for name, _ in res:
@@ -22,7 +27,7 @@ def spec_query(rt, queries):
                                           for e in rq.entries), default=0))
     ready = [t for t in core.tasks.values() if (t.state == "waiting" and t.is_ready()) or t.state == "prefilled"]     # prefilled tasks stay in the queues (taskqueue.rs:273-302)
     if not ready:
-        return [0 for _ in queries]
+        return None, None, None
     classes = []
     for c in range(len(core.rq_map)):
         vs = []
@@ -42,16 +47,29 @@ def spec_query(rt, queries):
     total = np.array(tot, dtype=np.uint64)
     wl = Workload(R, classes, total, total.copy(), np.array([t.rq_id for t in ready], dtype=np.uint32),
                   np.array([t.user_priority for t in ready], dtype=np.int32), worker_remaining_s=np.array(rem))
-    a, free_after = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), wl.worker_free)
-    loaded = np.bincount(a["worker"], minlength=len(tot)) > 0
-    # min_utilization (solver.rs:154-156, 479-518) as the shim applies it: at least min_cpus of new work, or nothing
-    for w, mu in enumerate(mus):
-        if mu > 0.001 and total[w, 0] != AMOUNT_MAX and loaded[w]:
-            cpu_total = float(total[w, 0]) / 1e4
-            new_cpus = (float(total[w, 0]) - float(free_after[w, 0])) / 1e4
-            if new_cpus < cpu_total * mu - 1e-9:
-                loaded[w] = False
-    return [int(sum(1 for w in range(len(tot)) if owner[w] == qi and loaded[w])) for qi in range(len(queries))]
+    return wl, np.array(mus, dtype=np.float32), owner
+
+
+def spec_query(rt, queries):
+    wl, mus, owner = query_workload(rt, queries)
+    if wl is None:
+        return [0 for _ in queries]
+    mu_arg = mus if (mus > 0.001).any() else None
+    a, free_after = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), wl.worker_free, min_utilization=mu_arg)
+    counts = np.bincount(a["worker"], minlength=wl.n_workers)
+    if _BACKEND == "gpu":
+        import workloads as WL
+        s = WL.gpu_scheduler(wl)
+        needed, got, n_total = s.new_worker_query(wl.worker_total, remaining_s=wl.worker_remaining_s, min_utilization=mus)
+        # a dry run: the ready set is untouched, a real tick over the same workers still assigns the same tasks
+        s.min_utilization = mus.copy()
+        m = s.run_scheduling()
+        s.close()
+        assert np.array_equal(got, counts), (got, counts)            # device == specification, worker by worker
+        assert n_total == int(counts.sum()) == m.n_assigned()
+        counts = got
+    loaded = counts > 0
+    return [int(sum(1 for w in range(wl.n_workers) if owner[w] == qi and loaded[w])) for qi in range(len(queries))]
 
 
 def q(res, partial=False, tl=None, n=1, mu=0.0):

@@ -11,7 +11,7 @@ import greedy_model as G
 import workloads as WL
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_drains.json")
-KEYS = sorted(k for k in json.load(open(GOLDEN)).keys() if not k.startswith("big_") or os.environ.get("HQS_BIG_DRAINS"))
+KEYS = sorted(k for k in json.load(open(GOLDEN)).keys() if not k.startswith(("big_", "w256_")) or os.environ.get("HQS_BIG_DRAINS"))
 
 
 @pytest.mark.parametrize("key", KEYS)

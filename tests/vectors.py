@@ -14,8 +14,12 @@ import numpy as np
 from workloads import FR, Workload
 
 
-def case(workers, tasks, expect, name, running=None, resources=1):
-    return {"workers": workers, "tasks": tasks, "expect": expect, "name": name, "running": running or {}, "R": resources}
+def case(workers, tasks, expect, name, running=None, resources=1, eq=None, worker_time=None, check=None):
+    """workers: per worker (cpus[, extra resource units]); tasks: (priority, class key); running: worker -> cpus in use;
+    eq: groups of interchangeable workers (the reference's eq_class); worker_time: worker -> remaining seconds;
+    check: extra predicate over (per-worker class-key lists) for cases that pin a property instead of a placement."""
+    return {"workers": workers, "tasks": tasks, "expect": expect, "name": name, "running": running or {}, "R": resources,
+            "eq": eq or [], "worker_time": worker_time or {}, "check": check}
 
 
 def c(cpus, **extra):          # single-variant request: cpus + {rid: units}
@@ -26,6 +30,22 @@ def c(cpus, **extra):          # single-variant request: cpus + {rid: units}
 
 def cv(*variants):             # variants: dicts rid -> units
     return tuple(tuple(sorted(v.items())) for v in variants)
+
+
+def cw(cpus, weight=1.0, time=0.0, all_cpus=False):     # single variant with weight / min_time / cpus = All
+    d = {} if all_cpus else {0: cpus}
+    return (tuple(sorted(d.items())) + (("w", weight), ("t", time)) + ((("all", 0),) if all_cpus else ()),)
+
+
+def _gap3(per):
+    """test_schedule_gap_filling3 :496-526: both 34-cpu workers are filled to 33 cpus and at most two of the lower-priority
+    3-cpu tasks land on each."""
+    for lst in per:
+        cpus = sum(dict(k[0])[0] for k, _p in lst)
+        low = sum(1 for k, p in lst if p == 9)
+        if cpus != 33 or low > 2:
+            return f"worker holds {cpus} cpus, {low} low-priority tasks"
+    return None
 
 
 CASES = [
@@ -84,6 +104,51 @@ CASES = [
     # test_schedule_some_tasks_running :332-366
     case([(3,)], [(1, c(3))], "count:0", "somerun-1", running={0: 1}),
     case([(3,)], [(1, c(2))], "count:1", "somerun-2", running={0: 1}),
+    case([(3,)], [(1, c(3)), (0, c(1))], "count:0", "somerun-3", running={0: 1}),
+    case([(3,)], [(0, c(2)), (0, c(1)), (0, c(3))], [[c(2)]], "somerun-4a", running={0: 1}),
+    case([(3,)], [(0, c(2)), (0, c(1)), (0, c(3))], [[c(1)]], "somerun-4b", running={0: 2}),
+    case([(3,)], [(0, c(2)), (0, c(1)), (0, c(3))], [[]], "somerun-4c", running={0: 3}),
+    # test_priority_switching :368-405: two workers x (w cpus, 10000 foo); a = 1 cpu, b = 1 cpu + 1 foo
+] + [
+    case([(w, 10000), (w, 10000)],
+         [(10, c(1))] * 3 + [(9, c(1, r1=1))] * 2 + [(8, c(1))] + [(7, c(1))] * 3 + [(6, c(1, r1=1))] + [(5, c(1, r1=1))] +
+         [(4, c(1))] * 5 + [(3, c(1, r1=1))], f"classcounts:{a},{b}", f"switch-{w}", resources=2)
+    for w, a, b in [(1, 2, 0), (2, 3, 1), (3, 4, 2), (4, 6, 2), (5, 7, 3), (6, 8, 4), (7, 10, 4), (8, 12, 4), (9, 12, 5), (10, 12, 5)]
+] + [
+    # test_schedule_gap_filling :410-449, last case
+    case([(8,)], [(1, c(3))] * 3 + [(2, c(1))] + [(0, c(1))] * 4, [[c(1), c(3), c(3), c(1)]], "gap-5"),
+    # test_schedule_gap_filling2 :461-494 (foo = resource 1): a = 1 cpu, b = 3 cpus, c = 4 cpus + 1 foo
+    case([(8, 0), (4, 1), (4, 1), (4, 1)], [(1, c(1))] * 7 + [(2, c(3))] * 3 + [(2, c(4, r1=1))] * 3, "classcounts:2,2,3", "gap2-plain", resources=2),
+    case([(8, 0), (4, 1), (4, 1), (4, 1)], [(1, c(1))] * 7 + [(2, c(3))] * 3 + [(2, c(4, r1=1))] * 3 + [(-1, c(3))] * 2 +
+         [(-2, c(4, r1=1))] * 3 + [(-3, c(1))] + [(-4, c(3))] * 2 + [(-5, c(4, r1=1))] * 3 + [(-6, c(1))], "classcounts:2,2,3", "gap2-extra", resources=2),
+    # test_schedule_gap_filling3 :496-526
+    case([(34,), (34,)], [(10, c(3))] * 5 + [(10, c(9))] * 6 + [(9, c(3))] * 5, "pred", "gap3", check=_gap3),
+    # test_schedule_gap_filling4 :528-565 (foo = 1, bar = 2, goo = 3)
+    case([(3, 10, 0, 10), (3, 10, 0, 10), (3, 10, 10, 0)], [(10, c(2, r3=1))] * 5 + [(9, c(1, r1=1))] * 2 + [(8, c(3, r1=1, r2=1))] * 10,
+         "classcounts:2,2,1", "gap4", resources=4),
+    # test_schedule_reservation_simple..5 :567-633
+    case([(3,), (3,)], [(3, c(3)), (2, c(2))], [[], [c(2)]], "resv-1", running={0: 1, 1: 1}, eq=[[0, 1]]),
+    case([(3,), (3,)], [(3, c(3)), (2, c(1)), (2, c(1))], [[], [c(1), c(1)]], "resv-2", running={0: 1, 1: 1}, eq=[[0, 1]]),
+    case([(3,), (3,)], [(3, c(3)), (2, c(1)), (2, c(1))], [[c(1)], []], "resv-3", running={0: 2, 1: 1}),
+    case([(4,), (3,), (3,), (3,)], [(4, c(3)), (3, c(3)), (3, c(3)), (2, c(1)), (2, c(1))], [[c(3)], [c(1)], [], []], "resv-4",
+         running={0: 1, 1: 2, 2: 2, 3: 1}),
+    case([(3,), (3,), (3,), (4,)], [(4, c(3)), (3, c(3)), (3, c(3)), (2, c(1)), (2, c(1))], [[c(1)], [], [], [c(3), c(1)]], "resv-5",
+         running={0: 2, 1: 2, 2: 1}),
+    # test_resource_time_assign / _balance1 :873-904 (worker time limits, task time requests)
+    case([(10,)], [(0, cw(1, time=170.0)), (0, cw(1)), (0, cw(1, time=99.0))], [[cw(1), cw(1, time=99.0)]], "time-assign", worker_time={0: 100.0}),
+    case([(1,), (1,), (1,)], [(0, cw(1, time=170.0)), (0, cw(1)), (0, cw(1, time=99.0))], [[cw(1)], [cw(1, time=170.0)], [cw(1, time=99.0)]],
+         "time-balance1", worker_time={0: 50.0, 1: 200.0, 2: 100.0}),
+    # test_schedule_variant_gap1 :1324-1351: 8 cpus OR 4 cpus + 2 gpus at priority 10, then 1-cpu tasks
+] + [
+    case([(14, 4)], [(10, cv({0: 8}, {0: 4, 1: 2}))] * 10 + [(0, c(1))] * 10, f"classcounts:*,{2 - r}", f"vargap-{r}", running={0: r}, resources=2)
+    for r in (0, 1, 2)
+] + [
+    # test_schedule_resource_weights1/2 :1353-1389
+    case([(4,)], [(0, cw(3)), (0, cw(2, weight=1.49))], [[cw(3)]], "weight1-a"),
+    case([(4,)], [(0, cw(3, weight=1.0)), (0, cw(2, weight=1.51))], [[cw(2, weight=1.51)]], "weight1-b"),
+    case([(12,)], [(0, cw(3, weight=1.1))] * 5 + [(0, cw(0, all_cpus=True))], [[cw(3, weight=1.1)] * 4], "weight2-a"),
+    case([(12,)], [(0, cw(3))] * 5 + [(0, cw(0, weight=1.1, all_cpus=True))], [[cw(0, weight=1.1, all_cpus=True)]], "weight2-b"),
+    # test_schedule_min_utilization3 :1447-1463 is in tests/test_gpu_edges.py (needs worker options)
 ]
 
 
@@ -95,7 +160,18 @@ def to_workload(cs) -> Tuple[Workload, List[Tuple]]:
     for prio, key in cs["tasks"]:
         if key not in keys:
             keys.append(key)
-            classes.append([{"amounts": {r: int(u * FR) for r, u in var}} for var in key])
+            vs = []
+            for var in key:
+                d = {"amounts": {r: int(u * FR) for r, u in var if isinstance(r, int)}}
+                opts = {r: u for r, u in var if not isinstance(r, int)}
+                if "w" in opts:
+                    d["weight"] = opts["w"]
+                if opts.get("t"):
+                    d["min_time_s"] = opts["t"]
+                if "all" in opts:
+                    d["all"] = (opts["all"],)
+                vs.append(d)
+            classes.append(vs)
         cls_of.append(keys.index(key))
     W = len(cs["workers"])
     total = np.zeros((W, R), dtype=np.uint64)
@@ -105,8 +181,13 @@ def to_workload(cs) -> Tuple[Workload, List[Tuple]]:
     free = total.copy()
     for w, used_cpus in cs["running"].items():
         free[w, 0] -= np.uint64(used_cpus * FR)
+    rem = None
+    if cs.get("worker_time"):
+        rem = np.full(W, np.inf)
+        for w, t in cs["worker_time"].items():
+            rem[w] = t
     wl = Workload(R, classes, total, free, np.array(cls_of, dtype=np.uint32),
-                  np.array([p for p, _ in cs["tasks"]], dtype=np.int32), name=cs["name"])
+                  np.array([p for p, _ in cs["tasks"]], dtype=np.int32), worker_remaining_s=rem, name=cs["name"])
     return wl, keys
 
 
@@ -119,6 +200,17 @@ def check(cs, wl, keys, a) -> Optional[str]:
         per[w].append(keys[wl.task_class[t]])
     if isinstance(exp, str):
         kind, _, arg = exp.partition(":")
+        if kind == "classcounts":      # assigned tasks per class, classes in order of first appearance ("*" = any)
+            got = np.bincount(wl.task_class[a["task"]], minlength=len(keys)).tolist()
+            want = arg.split(",")
+            ok = all(x == "*" or int(x) == g for x, g in zip(want, got))
+            return None if ok else f"class counts {got} != {want}"
+        if kind == "pred":
+            prio = wl.task_user_priority
+            perp = [[] for _ in range(W)]
+            for t, w in zip(a["task"].tolist(), a["worker"].tolist()):
+                perp[w].append((keys[wl.task_class[t]], int(prio[t])))
+            return cs["check"](perp)
         if kind == "count":
             return None if a.shape[0] == int(arg) else f"assigned {a.shape[0]} != {arg}"
         if kind == "perworker":
@@ -130,4 +222,11 @@ def check(cs, wl, keys, a) -> Optional[str]:
         raise ValueError(exp)
     got = [sorted(map(repr, p)) for p in per]
     want = [sorted(map(repr, e)) for e in exp]
+    for grp in cs.get("eq", []):       # interchangeable workers: compare as multisets
+        g_got = sorted(got[w] for w in grp)
+        g_want = sorted(want[w] for w in grp)
+        for w, x in zip(grp, g_got):
+            got[w] = x
+        for w, x in zip(grp, g_want):
+            want[w] = x
     return None if got == want else f"{got} != {want}"
