@@ -5,8 +5,9 @@
 constexpr u32 KEY_READY = 1u << 31;
 constexpr u32 KEY_DONE = 1u << 30;
 constexpr u32 KEY_VALID = 1u << 29;
+constexpr u32 KEY_PF = 1u << 28;          // ready AND prefilled on a worker (mapping.rs:156-230): still assignable
 constexpr u32 KEY_LEVEL_SHIFT = 14;
-constexpr u32 KEY_LEVEL_MASK = 0x7FFFu;
+constexpr u32 KEY_LEVEL_MASK = 0x3FFFu;     // bits 14..27 (levels <= HQS_MAX_GROUPS); bit 28 is KEY_PF
 constexpr u32 KEY_CLASS_MASK = 0x3FFFu;
 
 constexpr u32 SEG_CAP = 1u << 20;         // (group, worker, variant) count segments per tick
@@ -28,6 +29,8 @@ struct TickHeaderOut {
     u32 n_groups;
     u32 n_segments;
     u32 error;       // 1 = segment overflow, 2 = a grid wait timed out, 3 = out_cap too small (nothing was emitted)
+    u32 n_prefilled; // prefill records (kind 1) behind the assignments
+    u32 pad;
     unsigned long long dbg[8];   // clock64 phase lengths of the solver CTA (hqs_debug_read)
 };
 
@@ -93,7 +96,7 @@ __global__ void remove_k(u32 n, const u32* __restrict__ task, u32* __restrict__ 
     if (i >= n) return;
     u32 h = task[i];
     // the task leaves the table: not ready, and it no longer pins its priority level (level_live_k)
-    if (h < n_handles) key[h] &= ~(KEY_READY | KEY_VALID | KEY_DONE);
+    if (h < n_handles) key[h] &= ~(KEY_READY | KEY_VALID | KEY_DONE | KEY_PF);
 }
 
 // marks the (exact) priority levels that still have a task in the table
@@ -103,6 +106,14 @@ __global__ void level_live_k(u32 n_handles, const u32* __restrict__ key, const u
     if (h >= n_handles || !(key[h] & KEY_VALID)) return;
     const u32 lvl = find_level(levels, n_levels, prio[h], false);
     if (lvl != ~0u && !live[lvl]) live[lvl] = 1u;
+}
+
+// TaskQueue::check_dispose_prefill (taskqueue.rs:146-152): the prefilled tasks of one class go back to plain waiting
+__global__ void pf_dispose_k(u32 n_handles, u32* __restrict__ key, u32 cls) {
+    const u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_handles) return;
+    const u32 k = key[h];
+    if ((k & KEY_PF) && key_class(k) == cls) key[h] = k & ~KEY_PF;
 }
 
 __global__ void rearm_k(u32 n_handles, u32* __restrict__ key) {
@@ -139,7 +150,7 @@ __global__ void finished_k(u32 n, const u32* __restrict__ task, const u32* __res
                 ++made;
             }
         }
-        key[t] &= ~(KEY_VALID | KEY_DONE | KEY_READY);      // finished for good: the handle no longer pins its priority level
+        key[t] &= ~(KEY_VALID | KEY_DONE | KEY_READY | KEY_PF);      // finished for good: the handle no longer pins its priority level
     }
     made = __reduce_add_sync(0xffffffffu, made);
     if ((threadIdx.x & 31) == 0 && made) atomicAdd(n_new, made);

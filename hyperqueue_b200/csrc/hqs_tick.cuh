@@ -25,9 +25,10 @@ constexpr u32 TICK_WARPS = TICK_THREADS / 32;
 constexpr u32 EMIT_ROWS_MAX = 16;     // rows of 32 tasks per emit warp and chunk
 constexpr u32 EMIT_SEG_SMEM = 1024;   // count segments cached in shared memory by the emit step
 constexpr u32 CMD_PACK = 1, CMD_EMIT = 2, CMD_EXIT = 3;      // grid commands: cmd word = (sequence << 2) | type
-constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3;    // block commands inside the solver CTA
+constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3, BLK_PREFILL = 4;    // block commands inside the solver CTA
 constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4;
 constexpr u32 SM_NONE = 0xFFFFFFFFu;
+constexpr u32 PF_SEG_CAP = 1u << 18;  // prefill segments (eligible workers summed over classes) per tick
 constexpr u32 MU_MAX_PASSES = 8;      // restarts of the min-utilisation rule before the remaining violators are dropped
 
 struct TickSync {
@@ -44,6 +45,7 @@ struct TickSync {
 struct TickSmem {
     u32 fr, rem, unt, remtime, excl, touch, td, frontier, noresv, glist, gcl;     // always staged
     u32 classes, vorder, blocked, bef, loc;                        // optional
+    u32 kk, top, pflvl;                                            // proactive filling only
 };
 
 struct TickArgs {
@@ -80,6 +82,13 @@ struct TickArgs {
     hqs_assignment* out;
     u32 out_cap;
     u32* rem_scratch;        // [W][RT] u64 as u32 pairs: narrow remainders when they do not fit shared memory
+    // proactive filling (mapping.rs:156-230); pf_shift == 0: off.  With it on, every (level, class) splits into two groups,
+    // waiting tasks first, prefilled ones second (take_tasks, taskqueue.rs:320-355): g = (level * Q + class) * 2 + prefilled
+    u32 pf_shift, pf_reserve, pf_max;
+    const uint8_t* prefilled_wc;   // [W][Q] nonzero: the worker holds a prefilled task of the class (host mirror), or nullptr
+    uint4* gout2;            // [G] {end rank of the prefill range, offset of its records behind the assignments, first prefill segment, segments}
+    u32* pf_cum;             // [PF_SEG_CAP] prefill segments: inclusive end rank inside the group
+    u32* pf_wk;              //                                    worker
     // peer-to-peer count exchange (sharded tick without a host collective): x_world == 0 => off
     u32* x_peer[HQS_MAX_PEERS];   // base of every rank's exchange buffer (own included)
     u32* x_all;              // [G] out: sum over ranks
@@ -153,7 +162,7 @@ __device__ void count_chunk(const TickArgs& a, u32 b, u32* s_hist) {
         for (int j = 0; j < 8; ++j) {
             // keys inside one warp are mostly distinct (levels x classes), so plain shared-memory atomics
             // beat warp aggregation (match.any costs one round per distinct key)
-            if (k[j] & KEY_READY) atomicAdd(&s_hist[key_level(k[j]) * Q + key_class(k[j])], 1u);
+            if (k[j] & KEY_READY) atomicAdd(&s_hist[((key_level(k[j]) * Q + key_class(k[j])) << a.pf_shift) | ((k[j] >> 28) & a.pf_shift)], 1u);
         }
     }
     __syncthreads();
@@ -173,7 +182,7 @@ __device__ void count_chunk(const TickArgs& a, u32 b, u32* s_hist) {
 // HBM traffic: 4 B read per table slot (L2 hit: the count step read it microseconds ago), 8 B written per
 // assignment, 4 B key write-back per assignment.
 __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut* s_go, const u32* s_segc, const u32* s_segw,
-                           bool seg_smem, const u32* before) {
+                           bool seg_smem, const u32* before, u32 n_assigned) {
     const u32 G = a.G, Q = a.Q, nwarps = a.emit_warps, rows = a.rows;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // A chunk holds an assigned task only if, for some group, fewer than k[g] tasks of the group precede
@@ -184,7 +193,8 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
         bool mine = false;
         for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
             const u32 bef = before ? __ldcg(before + g) : 0u;
-            const u32 k = a.g_smem ? s_go[g].k : __ldcg(&a.gout[g].k);
+            u32 k = a.g_smem ? s_go[g].k : __ldcg(&a.gout[g].k);
+            if (a.pf_shift) { const u32 kpf = __ldcg(&a.gout2[g].x); k = k > kpf ? k : kpf; }      // the prefill range lies behind the assigned ranks
             mine |= __ldcg(row + g) + bef < k;
         }
         if (!__syncthreads_or(mine)) return;
@@ -207,7 +217,7 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
         peers[j] = 0;
         if (active && j < (int)rows) {                       // warp-uniform
             const bool ready = (kk[j] & KEY_READY) != 0;
-            const u32 g = key_level(kk[j]) * Q + key_class(kk[j]);
+            const u32 g = ((key_level(kk[j]) * Q + key_class(kk[j])) << a.pf_shift) | ((kk[j] >> 28) & a.pf_shift);
             const u32 act = __ballot_sync(0xffffffffu, ready);
             u32 pm = same_key_lanes(act, g, a.nbits);
             if (!ready) pm = 0;
@@ -234,7 +244,7 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
         if (active && j < (int)rows) {                       // warp-uniform
             const u32 i = wbeg + j * 32 + lane;
             const u32 k = kk[j], pm = peers[j];
-            const u32 g = key_level(k) * Q + key_class(k);
+            const u32 g = ((key_level(k) * Q + key_class(k)) << a.pf_shift) | ((k >> 28) & a.pf_shift);
             if (pm) {
                 const u32 leader = __ffs(pm) - 1;
                 u32 r0 = 0;
@@ -275,9 +285,31 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
                         asg.task = i;
                         asg.worker = (uint16_t)(wv & 0xFFFFu);
                         asg.variant = (uint8_t)((wv >> 16) & 0xFFu);
-                        asg.kind = 0;
+                        asg.kind = (k & KEY_PF) ? 2 : 0;                      // a prefilled task: retract + redirect (mapping.rs:63-101)
                         a.out[oi] = asg;
-                        a.key[i] = (k & ~KEY_READY) | KEY_DONE;               // Waiting -> Assigned
+                        a.key[i] = (k & ~(KEY_READY | KEY_PF)) | KEY_DONE;    // Waiting / Prefilled -> Assigned / Retracting
+                    }
+                } else if (a.pf_shift && !(k & KEY_PF)) {
+                    // proactive filling: the waiting tasks right behind the assigned ones go to the workers that just
+                    // received tasks of the class; they stay ready
+                    const uint4 g2 = __ldcg(a.gout2 + g);
+                    if (r_loc + bef < g2.x) {
+                        const u32 r = r_loc + bef;
+                        u32 lo = g2.z, hi = g2.z + g2.w;
+                        while (lo < hi) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (__ldcg(a.pf_cum + mid) > r) hi = mid; else lo = mid + 1;
+                        }
+                        const u32 oi = n_assigned + g2.y + (r - go.k);
+                        if (oi < a.out_cap) {
+                            hqs_assignment asg;
+                            asg.task = i;
+                            asg.worker = (uint16_t)__ldcg(a.pf_wk + lo);
+                            asg.variant = 0xFF;                                   // ComputeTasks with variant = None
+                            asg.kind = 1;
+                            a.out[oi] = asg;
+                            a.key[i] = k | KEY_PF;
+                        }
                     }
                 }
             }
@@ -381,7 +413,8 @@ __device__ void worker_cta(const TickArgs& a, unsigned char* smem) {
                     if (seg_smem)
                         for (u32 i = threadIdx.x; i < n_seg; i += blockDim.x) { s_segc[i] = __ldcg(a.seg_cum + i); s_segw[i] = __ldcg(a.seg_wv + i); }
                     __syncthreads();
-                    for (u32 b = me; b < a.P; b += nW) emit_chunk(a, b, s_cnt, s_go, s_segc, s_segw, seg_smem, before);
+                    const u32 n_assigned = __ldcg(&a.hdr->n_assigned);
+                    for (u32 b = me; b < a.P; b += nW) emit_chunk(a, b, s_cnt, s_go, s_segc, s_segw, seg_smem, before, n_assigned);
                 }
             } else if (threadIdx.x == 0) {
                 atomicExch(&a.sync->error, 2u);
@@ -411,7 +444,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     __shared__ u32 s_wcnt[TICK_WARPS];
     __shared__ u32 s_pkpos[PACK_MAX_CAND], s_pknseg[PACK_MAX_CAND], s_pkseglo[PACK_MAX_CAND], s_pkex[PACK_MAX_CAND], s_cbase[PACK_MAX_CAND + 1];
     __shared__ u32 s_blk[8];            // block command: type, li, lj, seg region base, phi (2 words), n_packs
-    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks, s_partial;
+    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks, s_partial, s_npref;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 W = a.W, Q = a.Q, R = a.R, G = a.G;
     const u32 nW = gridDim.x - 1;
@@ -437,6 +470,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     const uint8_t* blocked = a.blocked ? (a.sm.blocked != SM_NONE ? smem + a.sm.blocked : a.blocked) : nullptr;
     u32* s_bef = a.sm.bef != SM_NONE ? reinterpret_cast<u32*>(smem + a.sm.bef) : nullptr;
     u32* s_loc = a.sm.loc != SM_NONE ? reinterpret_cast<u32*>(smem + a.sm.loc) : nullptr;
+    u32* s_kk = a.pf_shift ? reinterpret_cast<u32*>(smem + a.sm.kk) : nullptr;          // [L*Q*2] tasks assigned per list entry (prefill)
+    u32* s_top = a.pf_shift ? reinterpret_cast<u32*>(smem + a.sm.top) : nullptr;        // [Q] best level with waiting tasks left
+    u32* s_pflvl = a.pf_shift ? reinterpret_cast<u32*>(smem + a.sm.pflvl) : nullptr;    // [Q] level of the class's prefilled tasks
 
     auto exact_of = [&](AT f, u32 w, int r) -> u64 {
         if constexpr (NARROW) return f == AMAX ? HQS_AMOUNT_MAX : (u64)f * a.gscale[r] + p_rem[(size_t)w * RT + r];
@@ -481,7 +517,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     };
 
     // ---- prologue A: staging (overlaps the histogram of the worker CTAs)
-    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; s_partial = 0; }
+    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; s_partial = 0; s_npref = 0; }
     if (tid < HQS_MAX_RESOURCES) { s_totmax[tid] = 0; s_D[tid] = 0; s_C[tid] = 0; }
     if (a.sm.classes != SM_NONE) {
         const uint4* src = reinterpret_cast<const uint4*>(a.classes);
@@ -520,7 +556,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         }
     }
     // groups without ready tasks keep k = 0 (the emit step's chunk filter reads k of every group)
-    for (u32 g = tid; g < G; g += blockDim.x) a.gout[g].k = 0;
+    for (u32 g = tid; g < G; g += blockDim.x) { a.gout[g].k = 0; if (a.pf_shift) a.gout2[g] = make_uint4(0, 0, 0, 0); }
     __syncthreads();
     sum_free_block();
 
@@ -574,7 +610,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     // ---- prologue C: compact the non-empty groups in processing order: level asc (= priority desc), then the
     //      tick's class order.  Every warp owns a contiguous range of positions; two passes, one barrier.
     {
-        const u32 n_pos = a.L * Q;
+        const u32 n_pos = (a.L * Q) << a.pf_shift;
         const u32 seg = ((n_pos + TICK_WARPS - 1) / TICK_WARPS + 31) & ~31u;      // positions per warp, multiple of 32
         u32 nn[HQS_MAX_GROUPS / TICK_WARPS / 32], gg[HQS_MAX_GROUPS / TICK_WARPS / 32];
         u32 cnt = 0;
@@ -583,8 +619,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             nn[i] = 0; gg[i] = 0;
             const u32 pos = warp * seg + i * 32 + lane;
             if ((u32)i * 32 < seg && pos < n_pos) {
-                const u32 lvl = pos / Q, j = pos - lvl * Q;
-                gg[i] = lvl * Q + a.order[j];
+                const u32 pos2 = pos >> a.pf_shift;                   // (level, class position); the low bit of pos: prefilled sub-group
+                const u32 lvl = pos2 / Q, j = pos2 - lvl * Q;
+                gg[i] = ((lvl * Q + a.order[j]) << a.pf_shift) | (pos & a.pf_shift);
                 nn[i] = __ldcg(tot_all + gg[i]);
             }
             cnt += __popc(__ballot_sync(0xffffffffu, nn[i] != 0));
@@ -600,7 +637,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                 const u32 slot = off + __popc(bal & ((1u << lane) - 1));
                 const u32 g = gg[i];
                 s_glist[slot] = make_uint2(g, nn[i]);
-                s_gcl[slot] = (g % Q) | ((g / Q) << 16);
+                s_gcl[slot] = ((g >> a.pf_shift) % Q) | (((g >> a.pf_shift) / Q) << 16);
                 if (before) {
                     if (s_bef) { s_bef[slot] = __ldcg(before + g); s_loc[slot] = __ldcg(a.total_local + g); }
                 }
@@ -671,6 +708,84 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             for (u32 c = tid; c < Q; c += blockDim.x) { s_front[c] = 0; s_noresv[c] = 0; }
             for (u32 w = tid; w < W; w += blockDim.x)
                 if (s_excl[w] == 2) s_excl[w] = 0;         // reservations are made again by the new pass
+            bar_named(2, TICK_THREADS);
+            return;
+        }
+        if (cmd == BLK_PREFILL) {
+            // ---- proactive filling (mapping.rs:156-230; specification: tests/greedy_model.py::_with_prefill).  For every
+            //      class whose best level with waiting (not prefilled) tasks left is the best one over all classes:
+            //      size = waiting tasks left at that level - reserve (0 while the class holds prefilled tasks at another
+            //      level); eligible workers = those that got an assignment of the class in this tick and hold no prefilled
+            //      task of it; each gets min(size / eligible, max) of the next waiting tasks.  Result: a prefill range behind
+            //      the assigned ranks of the (level, class) group, as segments of its own (gout2, pf_cum, pf_wk).
+            const u32 pfs = a.pf_shift;
+            for (u32 c = tid; c < Q; c += blockDim.x) { s_top[c] = 0xFFFFFFFFu; s_pflvl[c] = 0xFFFFFFFFu; }
+            if (tid == 0) { s_blk[6] = 0xFFFFFFFFu; s_blk[7] = 0; s_qT[0] = 0; s_qT[1] = 0; }
+            bar_named(2, TICK_THREADS);
+            for (u32 e = tid; e < n_list; e += blockDim.x) {
+                const u32 c = s_gcl[e] & 0xFFFFu, lvl = s_gcl[e] >> 16;
+                const u32 left = s_glist[e].y - s_kk[e];
+                if (left) atomicMin((s_glist[e].x & pfs) ? &s_pflvl[c] : &s_top[c], lvl);
+            }
+            bar_named(2, TICK_THREADS);
+            u32 best = 0xFFFFFFFFu;
+            for (u32 c = tid; c < Q; c += blockDim.x) best = min(best, s_top[c]);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+            if (lane == 0 && best != 0xFFFFFFFFu) atomicMin(&s_blk[6], best);
+            bar_named(2, TICK_THREADS);
+            const u32 gtop = s_blk[6];
+            u32 pf_out = 0, pf_seg = 0;                                          // uniform running totals
+            if (gtop != 0xFFFFFFFFu) {
+                for (u32 c = 0; c < Q; ++c) {
+                    if (s_top[c] != gtop || (s_pflvl[c] != 0xFFFFFFFFu && s_pflvl[c] != gtop)) continue;      // uniform
+                    // the (gtop, c, waiting) entry
+                    bar_named(2, TICK_THREADS);                                  // the previous candidate's readers are done
+                    if (tid == 0) s_blk[7] = 0xFFFFFFFFu;
+                    for (u32 w = tid; w < W; w += blockDim.x) s_touch[w] = 0;     // reused: worker got an assignment of the class
+                    bar_named(2, TICK_THREADS);
+                    for (u32 e = tid; e < n_list; e += blockDim.x) {
+                        if ((s_gcl[e] & 0xFFFFu) != c || (s_glist[e].x & pfs)) continue;
+                        if ((s_gcl[e] >> 16) == gtop) s_blk[7] = e;
+                        if (s_kk[e]) {
+                            const uint4 go = *reinterpret_cast<const uint4*>(a.gout + s_glist[e].x);        // written by this CTA
+                            for (u32 q = 0; q < go.w; ++q) s_touch[a.seg_wv[go.z + q] & 0xFFFFu] = 1;
+                        }
+                    }
+                    bar_named(2, TICK_THREADS);
+                    const u32 et = s_blk[7];
+                    const u32 k = s_kk[et], left = s_glist[et].y - k;
+                    if (left <= a.pf_reserve) continue;                          // uniform
+                    const u32 size = left - a.pf_reserve;
+                    // eligible workers in ascending order (warp 0 compacts tile by tile into s_td, free at this point)
+                    if (warp == 0) {
+                        u32 n_el = 0;
+                        for (u32 tile = 0; tile < n_tiles; ++tile) {
+                            const u32 w = tile * 32 + lane;
+                            const bool el = w < W && s_touch[w] && !(a.prefilled_wc && a.prefilled_wc[(size_t)w * Q + c]);
+                            const u32 em = __ballot_sync(0xffffffffu, el);
+                            if (el) s_td[n_el + __popc(em & ((1u << lane) - 1))] = (unsigned short)w;
+                            n_el += __popc(em);
+                        }
+                        if (lane == 0) s_qT[2] = n_el;
+                    }
+                    bar_named(2, TICK_THREADS);
+                    const u32 n_el = (u32)s_qT[2];
+                    if (n_el == 0) continue;                                     // uniform
+                    const u32 ps = min(size / n_el, a.pf_max);
+                    if (ps == 0 || pf_seg + n_el > PF_SEG_CAP) continue;         // uniform
+                    for (u32 i = tid; i < n_el; i += blockDim.x) {
+                        a.pf_cum[pf_seg + i] = k + (i + 1) * ps;
+                        a.pf_wk[pf_seg + i] = s_td[i];
+                    }
+                    if (tid == 0) a.gout2[s_glist[et].x] = make_uint4(k + n_el * ps, pf_out, pf_seg, n_el);
+                    pf_out += n_el * ps;
+                    pf_seg += n_el;
+                    bar_named(2, TICK_THREADS);
+                }
+            }
+            if (tid == 0) s_blk[7] = pf_out;
+            __threadfence();
             bar_named(2, TICK_THREADS);
             return;
         }
@@ -1102,6 +1217,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             cur_tile = 0xFFFFFFFFu;
                         }
                         const u32 k = n_all - remaining;
+                        if (s_kk && lane == 0) s_kk[e] = k;
                         u32 k_loc = k;
                         if (before) {
                             const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
@@ -1299,6 +1415,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     }
                     if (remaining && s_partial && !s_noresv[c]) reserve_for(c, n_all, remaining);
                     const u32 k = n_all - remaining;
+                    if (s_kk && lane == 0) s_kk[e] = k;
                     // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)
                     u32 k_loc = k;
                     if (before) {
@@ -1348,15 +1465,25 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             bar_named(1, TICK_THREADS);
             block_work(BLK_RESTART);
         }
+        u32 n_prefilled = 0;
+        if (a.pf_shift && a.pf_max && (a.flags & TF_EMIT) && !before) {
+            if (lane == 0) s_blk[0] = BLK_PREFILL;
+            __syncwarp();
+            bar_named(1, TICK_THREADS);
+            block_work(BLK_PREFILL);
+            n_prefilled = s_blk[7];
+        }
         if (lane == 0) s_blk[0] = BLK_END;
         __syncwarp();
         // ---- release the worker CTAs as early as possible: they need the group records, the segments and n_segments
         u32 err = s_err ? 2u : (seg_overflow ? 1u : 0u);
-        if (!err && n_assigned > a.out_cap && (a.flags & TF_EMIT)) err = 3u;
+        if (!err && n_assigned + n_prefilled > a.out_cap && (a.flags & TF_EMIT)) err = 3u;
         if (lane == 0) {
             a.hdr->n_segments = n_segments;
             a.hdr->n_assigned = n_assigned;
+            a.hdr->n_prefilled = n_prefilled;
             a.hdr->error = err;
+            s_npref = n_prefilled;
             __threadfence();
             const u32 seq = s_npacks + 1;
             st_release(&a.sync->cmd, (seq << 2) | ((err == 0 && (a.flags & TF_EMIT)) ? CMD_EMIT : CMD_EXIT));
@@ -1392,6 +1519,8 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         h.n_groups = n_list;
         h.n_segments = n_segments;
         h.error = err;
+        h.n_prefilled = s_npref;
+        h.pad = 0;
         h.dbg[0] = (unsigned long long)(t_counted - t_start);     // staging + wait for the histogram
         h.dbg[1] = (unsigned long long)(t_prologue - t_counted);  // exchange + compaction + demand
         h.dbg[2] = (unsigned long long)(t_solved - t_prologue);   // the solver warp

@@ -12,7 +12,7 @@
 // See DESIGN.md for the data layout, the kernels and their rooflines.
 //
 // Device data (all SoA, indexed by dense task handle h):
-//   key[h]   u32  bit31 READY | bit30 DONE (assigned by a tick) | bit29 VALID | level(15) | class(14)
+//   key[h]   u32  bit31 READY | bit30 DONE (assigned by a tick) | bit29 VALID | bit28 PREFILLED | level(14) | class(14)
 //   prio[h]  u64  tako Priority (only read when the level table changes)
 //   deps[h]  u32  unfinished dependencies (DAG mode), cons_off/cons: CSR of consumers
 // One tick = ONE cooperative kernel (tick_k, hqs_tick.cuh):
@@ -119,6 +119,10 @@ struct hqs_ctx {
     bool sync_dirty = true;             // the counters must be zeroed before the next launch (first tick / after a failed one)
     u64* d_pk_fr = nullptr; u32* d_pk_quota = nullptr; u32* d_pk_taken = nullptr; u32* d_pk_cand = nullptr; u32* d_pk_meta = nullptr;
     u32* d_rem_scratch = nullptr; uint8_t* d_excl = nullptr;
+    // proactive filling
+    u32 pf_reserve = 0, pf_max = 0;     // SchedulerConfig::proactive_filling_reserve / _max (state.rs:14-21); max == 0: off
+    uint4* d_gout2 = nullptr; u32* d_pf_cum = nullptr; u32* d_pf_wk = nullptr;
+    std::vector<uint8_t> prefilled_wc; u32 prefilled_W = 0;   // host mirror for the next tick: [W][Q]
     u32* d_seg_cum = nullptr; u32* d_seg_wv = nullptr;
     hqs_assignment* d_out = nullptr; u32 out_cap_dev = 0;
     TickHeaderOut* d_hdr = nullptr;
@@ -324,6 +328,9 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
             CU(cudaMemsetAsync(ctx->d_total, 0, ng * sizeof(u32), ctx->stream));
             CU(cudaMalloc(&ctx->d_gout, ng * sizeof(GroupOut)));
             CU(cudaMemsetAsync(ctx->d_gout, 0, ng * sizeof(GroupOut), ctx->stream));
+            if (ctx->d_gout2) CU(cudaFree(ctx->d_gout2));
+            CU(cudaMalloc(&ctx->d_gout2, ng * sizeof(uint4)));
+            CU(cudaMemsetAsync(ctx->d_gout2, 0, ng * sizeof(uint4), ctx->stream));
         }
         ctx->G_cap = ng; ctx->P_cap = np;
     }
@@ -340,6 +347,8 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
         CU(cudaMalloc(&ctx->d_pk_meta, 2 * sizeof(u32)));
         CU(cudaMalloc(&ctx->d_rem_scratch, (size_t)HQS_MAX_WORKERS * HQS_MAX_RESOURCES * sizeof(u64)));
         CU(cudaMalloc(&ctx->d_excl, HQS_MAX_WORKERS));
+        CU(cudaMalloc(&ctx->d_pf_cum, PF_SEG_CAP * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_pf_wk, PF_SEG_CAP * sizeof(u32)));
         ctx->sync_dirty = true;
     }
     if (!ctx->h_hdr) {
@@ -359,10 +368,10 @@ int ensure_tick_buffers(hqs_ctx* ctx, u32 G, u32 P, u32 W, u32 out_cap) {
 }
 
 struct TickLayout {
-    size_t off_free, off_total, off_rem, off_order, off_vorder, off_mu, off_blocked, bytes;
+    size_t off_free, off_total, off_rem, off_order, off_vorder, off_mu, off_blocked, off_pfwc, bytes;
 };
 
-TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
+TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked, bool pfwc = false) {
     TickLayout l;
     size_t o = 0;
     l.off_free = o; o += (size_t)W * R * 8;
@@ -373,6 +382,8 @@ TickLayout tick_layout(u32 W, u32 R, u32 Q, bool blocked) {
     l.off_vorder = o; o += (size_t)Q * HQS_MAX_VARIANTS;
     o = (o + 15) & ~size_t(15);
     l.off_blocked = o; if (blocked) o += (size_t)W * Q;
+    o = (o + 15) & ~size_t(15);
+    l.off_pfwc = o; if (pfwc) o += (size_t)W * Q;
     l.bytes = (o + 15) & ~size_t(15);
     return l;
 }
@@ -436,7 +447,7 @@ struct TickGeom { u32 G, L, P, chunk, rows, emit_warps, g_smem, nbits; size_t wo
 TickGeom tick_geom(const hqs_ctx* ctx) {
     TickGeom t;
     t.L = std::max<u32>((u32)ctx->dev_levels.size(), 1);
-    t.G = t.L * std::max<u32>(ctx->Q, 1);
+    t.G = (t.L * std::max<u32>(ctx->Q, 1)) << (ctx->pf_max ? 1 : 0);      // proactive filling: waiting / prefilled sub-groups
     t.nbits = 1;
     while ((1u << t.nbits) < t.G) t.nbits++;
     // emit step shared memory: warps * G counters (+ G solver records) + the segment cache
@@ -475,7 +486,8 @@ int ensure_tickin(hqs_ctx* ctx, size_t bytes) {
 int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64* free_rw, const u64* total_rw,
                       const uint8_t* blocked, TickLayout* lay_out, bool* has_mu, bool* any_time) {
     const u32 R = ctx->R, Q = ctx->Q;
-    const TickLayout lay = tick_layout(W, R, Q, blocked != nullptr);
+    const bool pfwc = ctx->pf_max && ctx->prefilled_W == W && ctx->prefilled_wc.size() == (size_t)W * Q;
+    const TickLayout lay = tick_layout(W, R, Q, blocked != nullptr, pfwc);
     int rc = ensure_tickin(ctx, lay.bytes);
     if (rc) return rc;
     unsigned char* h = ctx->h_tickin;
@@ -509,8 +521,10 @@ int upload_tick_input(hqs_ctx* ctx, u32 W, const hqs_worker* workers, const u64*
         // ABI bit index ((w*Q + c) * HQS_MAX_VARIANTS + v) with HQS_MAX_VARIANTS == 8: one byte per (w, c)
         memcpy(h + lay.off_blocked, blocked, (size_t)W * Q);
     }
+    if (pfwc) memcpy(h + lay.off_pfwc, ctx->prefilled_wc.data(), (size_t)W * Q);
+    ctx->h_small[11] = pfwc ? 1u : 0u;
     if (!ctx->zero_copy) CU(cudaMemcpyAsync(ctx->d_tickin, h, lay.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    else if (blocked) CU(cudaMemcpyAsync(ctx->d_tickin + lay.off_blocked, h + lay.off_blocked, (size_t)W * Q, cudaMemcpyHostToDevice, ctx->stream));
+    else if (blocked || pfwc) CU(cudaMemcpyAsync(ctx->d_tickin + lay.off_blocked, h + lay.off_blocked, lay.bytes - lay.off_blocked, cudaMemcpyHostToDevice, ctx->stream));
     *lay_out = lay;
     *has_mu = mu_any;
     *any_time = time_any;
@@ -586,6 +600,9 @@ TickArgs base_args(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay
     a.pk.fr = ctx->d_pk_fr; a.pk.quota = ctx->d_pk_quota; a.pk.taken = ctx->d_pk_taken;
     a.pk.cand = ctx->d_pk_cand; a.pk.meta = ctx->d_pk_meta;
     a.excl_glob = ctx->d_excl;
+    a.pf_shift = ctx->pf_max ? 1 : 0; a.pf_reserve = ctx->pf_reserve; a.pf_max = ctx->pf_max;
+    a.prefilled_wc = ctx->h_small[11] ? ctx->d_tickin + lay.off_pfwc : nullptr;
+    a.gout2 = ctx->d_gout2; a.pf_cum = ctx->d_pf_cum; a.pf_wk = ctx->d_pf_wk;
     return a;
 }
 
@@ -593,7 +610,7 @@ TickArgs base_args(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay
 size_t solver_layout(const hqs_ctx* ctx, TickArgs& a, size_t budget, bool sharded) {
     const u32 W = a.W, Q = a.Q, RT = ctx->RT;
     const size_t at = ctx->tick_narrow ? 4 : 8;
-    const u32 n_pos = a.L * Q;
+    const u32 n_pos = (a.L * Q) << a.pf_shift;
     size_t o = 0;
     auto put = [&](size_t bytes) { const size_t at_ = o; o = (o + bytes + 15) & ~size_t(15); return (u32)at_; };
     a.sm.fr = put((size_t)W * RT * at);
@@ -606,6 +623,8 @@ size_t solver_layout(const hqs_ctx* ctx, TickArgs& a, size_t budget, bool sharde
     a.sm.noresv = put(Q);
     a.sm.glist = put((size_t)n_pos * 8);
     a.sm.gcl = put((size_t)n_pos * 4);
+    a.sm.kk = a.sm.top = a.sm.pflvl = SM_NONE;
+    if (a.pf_shift) { a.sm.kk = put((size_t)n_pos * 4); a.sm.top = put((size_t)Q * 4); a.sm.pflvl = put((size_t)Q * 4); }
     auto opt = [&](size_t bytes, bool wanted) -> u32 {
         if (!wanted || o + bytes + 16 > budget) return SM_NONE;
         return put(bytes);
@@ -763,7 +782,7 @@ void hqs_destroy(hqs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* dev_ptrs[] = {ctx->d_classes, ctx->d_classes32, ctx->d_levels, ctx->d_key, ctx->d_prio, ctx->d_deps, ctx->d_cons_off,
                         ctx->d_cons, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_newcnt,
-                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_rem_scratch, ctx->d_excl, ctx->d_seg_cum,
+                        ctx->d_newprio, ctx->d_table, ctx->d_total, ctx->d_gout, ctx->d_rem_scratch, ctx->d_excl, ctx->d_gout2, ctx->d_pf_cum, ctx->d_pf_wk, ctx->d_seg_cum,
                         ctx->d_seg_wv, ctx->d_out, ctx->d_hdr, ctx->d_free_after, ctx->d_tickin, ctx->d_sync, ctx->d_pk_fr,
                         ctx->d_pk_quota, ctx->d_pk_taken, ctx->d_pk_cand, ctx->d_pk_meta};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
@@ -989,6 +1008,34 @@ int hqs_ready_remove(hqs_ctx* ctx, uint32_t n, const uint32_t* task) {
     return HQS_OK;
 }
 
+int hqs_prefill_config(hqs_ctx* ctx, uint32_t reserve, uint32_t max_per_worker) {
+    if (!ctx) return HQS_E_INVALID;
+    if (ctx->tick_pending) return fail(ctx, HQS_E_STATE, "the previous tick has not been fetched");
+    ctx->pf_reserve = reserve;
+    ctx->pf_max = max_per_worker;
+    return HQS_OK;
+}
+
+int hqs_prefill_state(hqs_ctx* ctx, uint32_t n_workers, const uint8_t* prefilled_wc) {
+    if (!ctx) return HQS_E_INVALID;
+    if (!prefilled_wc || n_workers == 0) { ctx->prefilled_wc.clear(); ctx->prefilled_W = 0; return HQS_OK; }
+    if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
+    ctx->prefilled_wc.assign(prefilled_wc, prefilled_wc + (size_t)n_workers * ctx->Q);
+    ctx->prefilled_W = n_workers;
+    return HQS_OK;
+}
+
+int hqs_prefill_dispose(hqs_ctx* ctx, uint32_t class_id) {
+    if (!ctx) return HQS_E_INVALID;
+    if (class_id >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", class_id, ctx->Q);
+    if (!ctx->n_handles) return HQS_OK;
+    CU(cudaSetDevice(ctx->device));
+    pf_dispose_k<<<(ctx->n_handles + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_handles, ctx->d_key, class_id);
+    ctx->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    return HQS_OK;
+}
+
 int hqs_ready_rearm(hqs_ctx* ctx) {
     if (!ctx) return HQS_E_INVALID;
     if (!ctx->n_handles) return HQS_OK;
@@ -1102,14 +1149,16 @@ int hqs_tick_fetch(hqs_ctx* ctx, uint32_t out_cap, hqs_assignment* out, uint32_t
     int rc = wait_header(ctx, &hdr);
     if (rc) return rc;
     // error 3: the solver saw that out_cap is too small BEFORE the emit step: nothing was emitted, the ready set is intact
-    if (hdr.error == 3 || hdr.n_assigned > out_cap || (hdr.n_assigned && !out))
-        return fail(ctx, HQS_E_OVERFLOW, "out_cap=%u too small for %u assignments", out_cap, hdr.n_assigned);
+    const u32 n_rec = hdr.n_assigned + hdr.n_prefilled;           // assignments (kind 0 / 2), then prefills (kind 1)
+    if (hdr.error == 3 || n_rec > out_cap || (n_rec && !out))
+        return fail(ctx, HQS_E_OVERFLOW, "out_cap=%u too small for %u assignments + %u prefills", out_cap, hdr.n_assigned, hdr.n_prefilled);
     if (free_after) memcpy(free_after, ctx->h_hdr + sizeof(TickHeaderOut), (size_t)ctx->last_W * ctx->R * 8);
-    if (hdr.n_assigned) {
-        CU(cudaMemcpyAsync(out, ctx->d_out, (size_t)hdr.n_assigned * sizeof(hqs_assignment), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_rec) {
+        CU(cudaMemcpyAsync(out, ctx->d_out, (size_t)n_rec * sizeof(hqs_assignment), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    if (out_n) *out_n = hdr.n_assigned;
+    ctx->prefilled_wc.clear(); ctx->prefilled_W = 0;             // the mirror is per tick
+    if (out_n) *out_n = n_rec;
     return HQS_OK;
 }
 

@@ -59,15 +59,44 @@ class WorkerTaskMapping:
     worker_ids: np.ndarray
     free_after: np.ndarray                        # [W][R] u64
 
+    retract_from: Optional[np.ndarray] = None     # for kind == 2 records: index of the worker the task was prefilled on
+
     def n_assigned(self) -> int:
-        return int(self.assignments.shape[0])
+        """Assignments of this tick: plain (kind 0) and redirected ones (kind 2); prefill records are not assignments."""
+        return int(np.count_nonzero(self.assignments["kind"] != 1))
+
+    def n_prefilled(self) -> int:
+        return int(np.count_nonzero(self.assignments["kind"] == 1))
+
+    def messages(self) -> Dict[int, Dict[str, list]]:
+        """WorkerTaskMapping::send_messages (mapping.rs:255-288) as data: worker_id -> {"retracts": [task handles] (one
+        RetractTasks message, sent first), "compute": [(task handle, variant or None)] (the ComputeTasks list: prefills
+        first with variant None, then the assigned tasks in priority-descending order; ComputeTasksBuilder splits it at
+        32 MiB of serialised size, server/task.rs:315-414)}.  Redirected tasks (kind 2) are NOT sent to their new worker
+        here: that happens when the old worker answers the retract (GpuScheduler.on_retract_response)."""
+        out: Dict[int, Dict[str, list]] = {}
+        a = self.assignments
+        def slot(widx):
+            return out.setdefault(int(self.worker_ids[widx]), {"retracts": [], "compute": []})
+        pf = a[a["kind"] == 1]
+        for t, w in zip(pf["task"].tolist(), pf["worker"].tolist()):
+            slot(w)["compute"].append((t, None))
+        for t, w, v, k in zip(a["task"].tolist(), a["worker"].tolist(), a["variant"].tolist(), a["kind"].tolist()):
+            if k == 0:
+                slot(w)["compute"].append((t, v))          # emission order is already priority-descending per worker
+        if self.retract_from is not None:
+            r2 = a[a["kind"] == 2]
+            for t, ow in zip(r2["task"].tolist(), self.retract_from.tolist()):
+                slot(ow)["retracts"].append(t)
+        return out
 
     def per_worker(self) -> Dict[int, List[Tuple[int, int]]]:
         """worker_id -> [(task handle, variant)] in emission order (priority descending)."""
         out: Dict[int, List[Tuple[int, int]]] = {}
         a = self.assignments
-        for t, w, v in zip(a["task"].tolist(), a["worker"].tolist(), a["variant"].tolist()):
-            out.setdefault(int(self.worker_ids[w]), []).append((t, v))
+        for t, w, v, k in zip(a["task"].tolist(), a["worker"].tolist(), a["variant"].tolist(), a["kind"].tolist()):
+            if k != 1:
+                out.setdefault(int(self.worker_ids[w]), []).append((t, v))
         return out
 
 
@@ -98,6 +127,11 @@ class GpuScheduler:
         self._task_variant = np.zeros(0, dtype=np.uint8)
         self._task_prio = np.zeros(0, dtype=np.uint64)
         self._out = np.zeros(1024, dtype=L.assignment_dtype)
+        # proactive filling: Worker::prefilled_tasks / SchedulerState::redirects (scheduler/state.rs:23-28), host side
+        self._prefill = (0, 0)
+        self._pf_worker = np.zeros(0, dtype=np.int64)     # per task: worker ID it is prefilled on, -1 = none
+        self.redirects: Dict[int, Tuple[int, int]] = {}   # retracting task -> (target worker id, variant)
+        self._retracting_from: Dict[int, int] = {}        # retracting task -> worker id it is being retracted from
 
     # ------------------------------------------------------------------------------------------
     def close(self) -> None:
@@ -201,6 +235,7 @@ class GpuScheduler:
             self._task_worker = np.concatenate([self._task_worker, np.full(m - self._task_worker.shape[0], -1, np.int64)])
             self._task_variant = np.concatenate([self._task_variant, np.zeros(m - self._task_variant.shape[0], np.uint8)])
             self._task_prio = np.concatenate([self._task_prio, np.zeros(m - self._task_prio.shape[0], np.uint64)])
+            self._pf_worker = np.concatenate([self._pf_worker, np.full(m - self._pf_worker.shape[0], -1, np.int64)])
 
     def add_ready_tasks(self, handles, rq_ids, priorities) -> None:
         h = np.ascontiguousarray(handles, dtype=np.uint32)
@@ -276,6 +311,15 @@ class GpuScheduler:
         total = np.ascontiguousarray(self.total)
         free_after = np.zeros_like(free)
         n = C.c_uint32(0)
+        if self._prefill[1] > 0:
+            # "worker w holds a prefilled task of class c" (Worker::prefilled_tasks), the host's view at tick start
+            held = np.nonzero(self._pf_worker >= 0)[0]
+            pfwc = np.zeros((nw, len(self._classes)), dtype=np.uint8)
+            if held.size:
+                widx = np.searchsorted(self.worker_ids, self._pf_worker[held])
+                ok = (widx < nw) & (self.worker_ids[np.minimum(widx, nw - 1)] == self._pf_worker[held])
+                pfwc[widx[ok], self._task_class[held[ok]]] = 1
+            self._check(self._lib.hqs_prefill_state(self._ctx, nw, L.ptr(np.ascontiguousarray(pfwc))))
         self._check(self._lib.hqs_tick(self._ctx, nw, L.ptr(w), L.ptr(free), L.ptr(total),
                                        L.ptr(blocked) if blocked is not None else None, out_cap,
                                        L.ptr(self._out), C.byref(n), L.ptr(free_after)))
@@ -283,10 +327,72 @@ class GpuScheduler:
         # WorkerConfiguration::min_utilization (solver.rs:154-156, 479-518) is enforced inside the tick kernel: a worker
         # that would receive less than its minimum is taken out of the solve, which then starts over
         self.free = free_after
+        retract_from = None
         if a.size:
-            self._task_worker[a["task"]] = a["worker"]
-            self._task_variant[a["task"]] = a["variant"]
-        return WorkerTaskMapping(a, self.worker_ids.copy(), free_after)
+            asg = a[a["kind"] != 1]
+            self._task_worker[asg["task"]] = asg["worker"]
+            self._task_variant[asg["task"]] = asg["variant"]
+            red = a[a["kind"] == 2]
+            if red.size:
+                # a prefilled task was assigned: RetractTasks to the worker that holds it, redirect to the new one; the
+                # new worker's resources are already taken (mapping.rs:49-101)
+                old = self._pf_worker[red["task"]].copy()
+                retract_from = np.searchsorted(self.worker_ids, old)
+                for t, ow, nwk, v in zip(red["task"].tolist(), old.tolist(), red["worker"].tolist(), red["variant"].tolist()):
+                    self.redirects[t] = (int(self.worker_ids[nwk]), int(v))
+                    self._retracting_from[t] = int(ow)
+                self._pf_worker[red["task"]] = -1
+            pf = a[a["kind"] == 1]
+            if pf.size:
+                self._pf_worker[pf["task"]] = self.worker_ids[pf["worker"]]
+        return WorkerTaskMapping(a, self.worker_ids.copy(), free_after, retract_from)
+
+    # proactive filling ------------------------------------------------------------------------------
+    def set_prefill(self, reserve: int, max_per_worker: int) -> None:
+        """SchedulerConfig::proactive_filling_reserve / _max (scheduler/state.rs:14-21; tako's defaults: 16 / 40)."""
+        self._prefill = (int(reserve), int(max_per_worker))
+        self._check(self._lib.hqs_prefill_config(self._ctx, int(reserve), int(max_per_worker)))
+
+    def prefilled_tasks(self, worker_id: int) -> np.ndarray:
+        return np.nonzero(self._pf_worker == worker_id)[0]
+
+    def on_task_running_prefilled(self, handle: int, variant: int) -> None:
+        """The worker started one of its prefilled tasks by itself (reactor.rs:263-345, RunningPrefilled): the task leaves
+        the ready set and takes the worker's resources."""
+        wid = int(self._pf_worker[handle])
+        assert wid >= 0, "task is not prefilled"
+        pos = int(np.searchsorted(self.worker_ids, wid))
+        self._pf_worker[handle] = -1
+        self._task_worker[handle] = pos
+        self._task_variant[handle] = variant
+        am = self._amount_tab[self._task_class[handle], variant]
+        self.free[pos] = np.where(self._all_tab[self._task_class[handle], variant], 0, self.free[pos] - np.minimum(self.free[pos], am))
+        self.remove_ready_tasks(np.array([handle], dtype=np.uint32))
+
+    def on_retract_response(self, worker_id: int, handles) -> Dict[int, List[Tuple[int, int]]]:
+        """on_retract_response (server/reactor.rs:452-498): the worker gave the listed tasks back.  A task with a redirect
+        becomes Assigned on its target (returned as target worker id -> [(task, variant)], one ComputeTasks message each);
+        without one it would wait again.  Tasks not being retracted from this worker are ignored."""
+        to_workers: Dict[int, List[Tuple[int, int]]] = {}
+        for t in np.asarray(handles).tolist():
+            if self._retracting_from.get(t) != worker_id:
+                continue
+            del self._retracting_from[t]
+            tgt = self.redirects.pop(t, None)
+            if tgt is not None:
+                to_workers.setdefault(tgt[0], []).append((t, tgt[1]))
+        return to_workers
+
+    def dispose_prefill(self, rq_id: int) -> Dict[int, List[int]]:
+        """TaskQueue::check_dispose_prefill (taskqueue.rs:146-152): a task of higher priority became ready, the class's
+        prefills are retracted and wait again.  Returns worker id -> [task handles] (RetractTasks messages)."""
+        held = np.nonzero((self._pf_worker >= 0) & (self._task_class[: self._pf_worker.shape[0]] == rq_id))[0]
+        out: Dict[int, List[int]] = {}
+        for t in held.tolist():
+            out.setdefault(int(self._pf_worker[t]), []).append(t)
+        self._pf_worker[held] = -1
+        self._check(self._lib.hqs_prefill_dispose(self._ctx, int(rq_id)))
+        return out
 
     def tasks_finished(self, handles, propagate: bool = False) -> int:
         """task_finished for a batch: returns the resources of each task to its worker

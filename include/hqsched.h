@@ -91,7 +91,10 @@ typedef struct {
     uint32_t task;     /* handle                                                         */
     uint16_t worker;   /* INDEX into the workers[] array of this tick (not worker_id)    */
     uint8_t variant;   /* ResourceVariantId                                              */
-    uint8_t kind;      /* 0 = assign (ComputeTasks with variant), 1 = prefill (reserved) */
+    uint8_t kind;      /* 0 = assign (ComputeTasks with the variant)
+                          1 = prefill (ComputeTasks with variant = None, mapping.rs:156-230): the task stays ready
+                          2 = the task was prefilled on another worker: RetractTasks to that worker (the host knows
+                              which) + redirect to `worker` / `variant` (mapping.rs:63-101)                   */
 } hqs_assignment;
 
 typedef struct {
@@ -157,8 +160,8 @@ int hqs_tasks_finished(hqs_ctx* ctx, uint32_t n, const uint32_t* task, uint32_t*
  *   total_rw[n_workers][R]        Worker::resources                          (worker.rs:69)
  *   blocked_wcv                   optional bitmask, bit index ((w * n_classes + c) * HQS_MAX_VARIANTS + v),
  *                                 LSB-first in bytes: Worker::blocked_requests (worker.rs:70,328-344)
- *   out[out_cap], *out_n          assignments, ordered by (priority desc, class order of this tick,
- *                                 handle asc) — per worker that is already the priority-descending
+ *   out[out_cap], *out_n          assignments (kind 0 / 2), ordered by (priority desc, class order of this tick,
+ *                                 handle asc), then the prefill records (kind 1) if proactive filling is on — per worker that is already the priority-descending
  *                                 order mapping.rs:125-128 sorts into
  *   free_after[n_workers][R]      optional: free vectors after the tick's assignments
  * Assigned tasks leave the ready set (Waiting -> Assigned, mapping.rs:55-66). */
@@ -216,6 +219,22 @@ int hqs_shard_tick_launch(hqs_ctx* ctx, uint32_t n_workers, const hqs_worker* wo
                           const uint64_t* total_rw, const uint8_t* blocked_wcv, uint32_t out_cap);
 /* Device pointer / length of the last tick's assignment buffer (for NCCL all-gather of results). */
 int hqs_device_result(hqs_ctx* ctx, const hqs_assignment** d_out, const uint32_t** d_out_n);
+
+/* Proactive filling (scheduler/mapping.rs:156-230, SchedulerConfig::proactive_filling_reserve / _max, state.rs:14-21;
+ * tako's defaults are 16 / 40).  Off (max = 0) unless configured.  With it on, a tick
+ *   - counts prefilled tasks as ready; inside one priority level the waiting tasks of a class go first, the prefilled
+ *     ones second (TaskQueue::take_tasks, taskqueue.rs:320-355); an assigned prefilled task comes out with kind = 2,
+ *   - appends, behind the assignments, kind = 1 records: for every class whose best level with waiting tasks is the best
+ *     over all classes, the workers that received an assignment of the class in this tick and hold no prefilled task of
+ *     it (hqs_prefill_state) each get min((waiting tasks of the level - reserve) / workers, max) of the next waiting tasks.
+ * The host keeps Worker::prefilled_tasks: it passes "worker w holds a prefilled task of class c" before each tick
+ * (hqs_prefill_state, bytes [n_workers][n_classes], consumed by the next tick), removes a prefilled task that a worker
+ * started with hqs_ready_remove, and calls hqs_prefill_dispose(class) where TaskQueue::check_dispose_prefill
+ * (taskqueue.rs:146-152: a task of higher priority became ready) retracts the class's prefills.
+ * Not available in sharded ticks. */
+int hqs_prefill_config(hqs_ctx* ctx, uint32_t reserve, uint32_t max_per_worker);
+int hqs_prefill_state(hqs_ctx* ctx, uint32_t n_workers, const uint8_t* prefilled_wc);
+int hqs_prefill_dispose(hqs_ctx* ctx, uint32_t class_id);
 
 /* Restores every task that earlier ticks assigned (DONE) to the ready state (benchmark and what-if use:
  * re-arm the same ready set without a new upload). */

@@ -61,8 +61,8 @@ for key, (kind, args, kwargs) in CASES.items():
         oracle_ticks, per_tick = out[key]["oracle_ticks"], None
     else:
         # 256-worker pools: HiGHS finds no incumbent inside the 2 s cap of ORACLE_FAST (4168 variables, 77 k rows in the
-        # first tick); 10 s and a 2 % gap do
-        opts = dict(time_limit=10.0, mip_rel_gap=0.02, accept_incumbent=True) if key.startswith("w256_") else None
+        # first tick); 20 s and a 2 % gap do
+        opts = dict(time_limit=20.0, mip_rel_gap=0.02, accept_incumbent=True) if key.startswith("w256_") else None
         oracle_ticks, per_tick = P.oracle_drain(wl, solver_opts=opts)
     model_ticks, _ = G.model_drain(wl)
     out[key] = {"args": args, "kwargs": kwargs, "oracle_ticks": oracle_ticks, "max_ticks": model_ticks,

@@ -341,7 +341,8 @@ def _pack_level(t: _Tick, groups: List[Tuple[int, int]], phi: float) -> Dict[Tup
 
 def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Optional[np.ndarray] = None,
                remaining_ms: Optional[np.ndarray] = None, pack: bool = True,
-               min_utilization: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+               min_utilization: Optional[np.ndarray] = None, prefill: Optional[Tuple[int, int]] = None,
+               pf_worker: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     """Returns (assignments in device emission order, free_after).
 
     min_utilization (solver.rs:154-156, 479-518): a worker either receives at least
@@ -350,9 +351,9 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
     W = free.shape[0]
     excluded = np.zeros(W, dtype=bool)
     for p in range(MU_MAX_PASSES):
-        a, fa = _solve_pass(wl, ready, free, levels, remaining_ms, pack, excluded)
+        a, fa = _solve_pass(wl, ready, free, levels, remaining_ms, pack, excluded, pf_worker)
         if min_utilization is None or p + 1 >= MU_MAX_PASSES:
-            return a, fa
+            return _with_prefill(wl, ready, a, levels, prefill, pf_worker), fa
         viol = False
         for w in range(W):
             mu = float(np.float32(min_utilization[w]))
@@ -365,15 +366,81 @@ def model_tick(wl: Workload, ready: np.ndarray, free: np.ndarray, levels: Option
                 excluded[w] = True
                 viol = True
         if not viol:
-            return a, fa
+            return _with_prefill(wl, ready, a, levels, prefill, pf_worker), fa
     raise AssertionError("unreachable")
+
+
+def _with_prefill(wl: Workload, ready: np.ndarray, a: np.ndarray, levels, prefill, pf_worker) -> np.ndarray:
+    """Proactive filling (mapping.rs:156-230) and the retract / redirect marking (mapping.rs:63-101) on top of a tick's
+    assignments.  pf_worker[t] = worker a ready task is prefilled on (-1: none) is updated in place:
+      * an assigned task that was prefilled comes out with kind = 2 (RetractTasks to its old worker + redirect to the
+        new one, even if they are the same worker, as in the reference) and is no longer prefilled,
+      * then, for every class whose best waiting (not prefilled) priority level is the best one over all classes:
+        size = waiting tasks of that level - reserve (0 if the class still has prefilled tasks at another level,
+        taskqueue.rs:237-253); eligible workers = those that received an ASSIGNMENT (kind 0) of the class in this tick and
+        held no prefilled task of it at tick start (the host's mirror; the reference looks after this tick's retracts);
+        each gets min(size // eligible, max) of the level's next waiting tasks in handle
+        order: records with kind = 1 after all assignments, classes ascending, workers ascending.  The tasks stay ready."""
+    if prefill is None or prefill[1] <= 0:
+        return a
+    reserve, pmax = prefill
+    if pf_worker is None:
+        raise ValueError("prefill needs the pf_worker state array")
+    W = wl.n_workers
+    out = a.copy()
+    pf_start = pf_worker.copy()          # "holds a prefilled task of the class" is the host's view at tick start
+    was_pf = pf_worker[out["task"]] >= 0
+    out["kind"][was_pf] = 2
+    pf_worker[out["task"][was_pf]] = -1
+    prio = wl.task_user_priority.astype(np.int64)
+    if levels is None:
+        levels = np.unique(prio)[::-1]
+    still = ready.copy()
+    still[out["task"]] = False
+    waiting = np.nonzero(still & (pf_worker < 0))[0]
+    if waiting.size == 0:
+        return out
+    lvl_of = {int(p): i for i, p in enumerate(np.asarray(levels).tolist())}
+    lv = np.array([lvl_of[int(p)] for p in prio[waiting]])
+    cls = wl.task_class[waiting]
+    top_c = {}
+    for c in np.unique(cls).tolist():
+        top_c[int(c)] = int(lv[cls == c].min())
+    g_top = min(top_c.values())
+    extra = []
+    for c in sorted(top_c):
+        if top_c[c] != g_top:
+            continue
+        pf_here = np.nonzero(ready & (pf_worker >= 0) & (wl.task_class == c))[0]
+        if pf_here.size and any(lvl_of[int(p)] != g_top for p in prio[pf_here]):
+            continue
+        cand = waiting[(cls == c) & (lv == g_top)]                    # ascending handle
+        size = cand.size - reserve
+        if size <= 0:
+            continue
+        got = np.unique(out["worker"][(out["kind"] == 0) & (wl.task_class[out["task"]] == c)])
+        elig = [int(w) for w in got.tolist() if not np.any((pf_start == w) & ready & (wl.task_class == c))]
+        if not elig:
+            continue
+        ps = min(size // len(elig), pmax)
+        if ps == 0:
+            continue
+        pos = 0
+        for w in elig:
+            for t in cand[pos: pos + ps].tolist():
+                extra.append((t, w, 0, 1))
+                pf_worker[t] = w
+            pos += ps
+    if extra:
+        out = np.concatenate([out, np.array(extra, dtype=assignment_dtype)])
+    return out
 
 
 MU_MAX_PASSES = 8
 
 
 def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remaining_ms, pack: bool,
-                excluded: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+                excluded: np.ndarray, pf_worker: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     W, R = free.shape
     prio = wl.task_user_priority.astype(np.int64)
     if levels is None:
@@ -395,8 +462,21 @@ def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remai
         if in_lvl.size == 0:
             continue
         cls_lvl = wl.task_class[in_lvl]
-        tasks_of = {c: in_lvl[cls_lvl == c] for c in order}
-        groups = [(c, int(tasks_of[c].size)) for c in order if tasks_of[c].size]
+        if pf_worker is None:
+            tasks_of = {c: in_lvl[cls_lvl == c] for c in order}
+            groups = [(c, int(tasks_of[c].size)) for c in order if tasks_of[c].size]
+            gkeys = [c for c, _ in groups]
+        else:
+            # prefilled tasks of a (level, class) come after its waiting ones (take_tasks, taskqueue.rs:320-355): two groups
+            pf_lvl = pf_worker[in_lvl] >= 0
+            tasks_of, groups, gkeys = {}, [], []
+            for c in order:
+                for pfb in (False, True):
+                    sel = in_lvl[(cls_lvl == c) & (pf_lvl == pfb)]
+                    if sel.size:
+                        tasks_of[(c, pfb)] = sel
+                        groups.append((c, int(sel.size)))
+                        gkeys.append((c, pfb))
         taken: Dict[Tuple[int, int], List[int]] = {}
         if not packed:
             n_cand = sum(len(t.am[c]) for c, _ in groups)
@@ -407,7 +487,7 @@ def _solve_pass(wl: Workload, ready: np.ndarray, free: np.ndarray, levels, remai
                     taken = _pack_level(t, groups, phi)
                     packed = True
         for gi, (c, n) in enumerate(groups):
-            tasks = tasks_of[c]
+            tasks = tasks_of[gkeys[gi]]
             pos = 0
             # cap what the workers took for this class at its count, (variant, worker) order; hand the
             # excess back
