@@ -209,7 +209,17 @@ WorkerTaskMapping GpuCore::run_scheduling(uint64_t now_ms) {
             if (b.first < Q) blocked[(size_t)i * Q + b.first] |= (uint8_t)(1u << b.second);
         ++i;
     }
-    if (out_.size() < tasks_.size()) out_.resize(tasks_.size());
+    if (out_.size() < tasks_.size() * (pf_max_ ? 2 : 1)) out_.resize(tasks_.size() * (pf_max_ ? 2 : 1));
+    if (pf_max_) {
+        // Worker::prefilled_tasks as the device needs it: does worker w hold a prefilled task of class c?
+        std::vector<uint8_t> pfwc((size_t)W * Q, 0);
+        for (const TaskState& t : tasks_)
+            if (t.live && t.prefilled_on >= 0) {
+                auto it = std::lower_bound(ids.begin(), ids.end(), (WorkerId)t.prefilled_on);
+                if (it != ids.end() && *it == (WorkerId)t.prefilled_on) pfwc[(size_t)(it - ids.begin()) * Q + t.rq] = 1;
+            }
+        hqs_prefill_state(ctx_, W, pfwc.data());
+    }
     uint32_t n = 0;
     const int rc = hqs_tick(ctx_, W, hw.data(), free_rw.data(), total_rw.data(), any_blocked ? blocked.data() : nullptr,
                             (uint32_t)out_.size(), out_.data(), &n, free_after.data());
@@ -223,6 +233,20 @@ WorkerTaskMapping GpuCore::run_scheduling(uint64_t now_ms) {
     for (uint32_t k = 0; k < n; ++k) {
         const hqs_assignment& a = out_[k];
         TaskState& t = tasks_[a.task];
+        if (a.kind == 1) {                                  // prefill: the task stays ready (mapping.rs:156-230)
+            t.prefilled_on = ids[a.worker];
+            mapping.workers[ids[a.worker]].prefills.push_back(t.id);
+            continue;
+        }
+        if (a.kind == 2) {                                  // was prefilled elsewhere: retract + redirect (mapping.rs:63-101)
+            mapping.workers[(WorkerId)t.prefilled_on].retracts.push_back(t.id);
+            redirects_[t.id.as_u64()] = {ids[a.worker], a.variant};
+            t.retracting_from = t.prefilled_on;
+            t.prefilled_on = -1;
+            t.worker = ids[a.worker];                       // the target's resources are taken already (free_after)
+            t.variant = a.variant;
+            continue;
+        }
         t.worker = ids[a.worker];
         t.variant = a.variant;
         mapping.workers[ids[a.worker]].assigned.emplace_back(t.id, a.variant);     // emission order = priority desc
@@ -233,6 +257,55 @@ WorkerTaskMapping GpuCore::run_scheduling(uint64_t now_ms) {
         ++i;
     }
     return mapping;
+}
+
+void GpuCore::set_scheduler_config(uint32_t proactive_filling_reserve, uint32_t proactive_filling_max) {
+    pf_max_ = proactive_filling_max;
+    if (hqs_prefill_config(ctx_, proactive_filling_reserve, proactive_filling_max) != HQS_OK) {
+        last_error_ = hqs_last_error(ctx_);
+        throw std::runtime_error("hqs_prefill_config: " + last_error_);
+    }
+}
+
+size_t GpuCore::n_prefilled(WorkerId id) const {
+    size_t n = 0;
+    for (const TaskState& t : tasks_) n += (t.live && t.prefilled_on == (int64_t)id) ? 1 : 0;
+    return n;
+}
+
+void GpuCore::on_task_running_prefilled(TaskId task, ResourceVariantId variant) {
+    auto it = handle_of_.find(task.as_u64());
+    if (it == handle_of_.end()) return;
+    TaskState& t = tasks_[it->second];
+    if (t.prefilled_on < 0) return;
+    auto wit = workers_.find((WorkerId)t.prefilled_on);
+    if (wit != workers_.end()) {
+        const hqs_variant& hv = classes_[t.rq].variants[variant];
+        for (uint32_t r = 0; r < R_; ++r) {                   // Worker::insert_sn_task (worker.rs:188-196)
+            if ((hv.all_mask >> r) & 1) wit->second.free[r] = 0;
+            else if (hv.amount[r] && wit->second.free[r] != HQS_AMOUNT_MAX) wit->second.free[r] -= std::min(wit->second.free[r], hv.amount[r]);
+        }
+    }
+    t.worker = t.prefilled_on; t.variant = variant; t.prefilled_on = -1;
+    const uint32_t h = it->second;
+    if (hqs_ready_remove(ctx_, 1, &h) != HQS_OK) { last_error_ = hqs_last_error(ctx_); log_error("hqs_ready_remove", last_error_.c_str()); }
+}
+
+std::map<WorkerId, std::vector<std::pair<TaskId, ResourceVariantId>>> GpuCore::on_retract_response(WorkerId worker, const std::vector<TaskId>& tasks) {
+    std::map<WorkerId, std::vector<std::pair<TaskId, ResourceVariantId>>> to_workers;
+    for (const TaskId& id : tasks) {
+        auto it = handle_of_.find(id.as_u64());
+        if (it == handle_of_.end()) continue;
+        TaskState& t = tasks_[it->second];
+        if (t.retracting_from != (int64_t)worker) continue;             // "Retracted task is in invalid state"
+        t.retracting_from = -1;
+        auto rd = redirects_.find(id.as_u64());
+        if (rd != redirects_.end()) {
+            to_workers[rd->second.first].emplace_back(id, rd->second.second);
+            redirects_.erase(rd);
+        }
+    }
+    return to_workers;
 }
 
 // task_finished (reactor.rs:500-580) -> Worker::remove_sn_task -> WorkerResources::add (workerload.rs:194-202):
@@ -394,6 +467,36 @@ extern "C" int hqshim_selftest(int device, int verbose) {
             ck.check(ok, "drain: capacities respected, no task twice, free vectors consistent");
             ck.check(ticks > 0 && ticks < 200, "drain: finished in a sane number of ticks");
             if (verbose) std::fprintf(stderr, "[shim selftest] drain took %zu ticks\n", ticks);
+        }
+        {   // proactive filling + retract / redirect, restated from test_prefill_basic and test_prefill_steal
+            // (test_scheduler_sn.rs:1168-1200, 1225-1306)
+            GpuCore core(1, device);
+            core.set_scheduler_config(4, 32);
+            const ResourceRqId c4 = core.get_or_create_resource_rq_id(cpus(4));
+            core.on_new_worker(50, {8 * FRACTIONS_PER_UNIT});
+            core.on_new_worker(51, {8 * FRACTIONS_PER_UNIT});
+            for (uint32_t t = 1; t <= 300; ++t) core.add_ready_task(TaskId{4, t}, c4, priority_from_user(0));
+            WorkerTaskMapping m = core.run_scheduling();
+            bool ok = m.workers.size() == 2;
+            for (const auto& kv : m.workers) ok &= kv.second.prefills.size() == 32 && kv.second.assigned.size() == 2 && kv.second.retracts.empty();
+            ck.check(ok, "prefill: 32 prefills + 2 assigned per worker");
+            ck.check(core.n_prefilled(50) == 32 && core.n_prefilled(51) == 32, "prefill: Worker::prefilled_tasks mirror");
+        }
+        {
+            GpuCore core(1, device);
+            core.set_scheduler_config(3, 6);
+            const ResourceRqId c1 = core.get_or_create_resource_rq_id(cpus(1));
+            core.on_new_worker(50, {1 * FRACTIONS_PER_UNIT});
+            for (uint32_t t = 1; t <= 9; ++t) core.add_ready_task(TaskId{5, t}, c1, priority_from_user(0));
+            WorkerTaskMapping m = core.run_scheduling();
+            ck.check(core.n_prefilled(50) == 5, "steal: 5 prefills on the only worker");
+            core.on_new_worker(51, {5 * FRACTIONS_PER_UNIT});
+            m = core.run_scheduling();
+            ck.check(m.workers[50].retracts.size() == 2 && m.workers[51].assigned.size() == 3, "steal: 2 retracts, 3 fresh tasks");
+            ck.check(core.redirects().size() == 2 && core.n_prefilled(50) == 3 && core.free_resources(51)[0] == 0, "steal: redirects and resources");
+            const TaskId t = m.workers[50].retracts[0];
+            auto sent = core.on_retract_response(50, {t});
+            ck.check(sent.size() == 1 && sent[51].size() == 1 && sent[51][0].first == t && core.redirects().size() == 1, "steal: retract response sends the task on");
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "[shim selftest] exception: %s\n", e.what());

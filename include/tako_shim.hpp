@@ -71,8 +71,10 @@ struct ResourceRequestVariants {          // request.rs:229-353
     std::vector<ResourceRequest> variants;
 };
 
-struct WorkerTaskUpdate {                 // mapping.rs:9-14 (prefills / retracts: not produced by this path yet)
+struct WorkerTaskUpdate {                 // mapping.rs:9-14
     std::vector<std::pair<TaskId, ResourceVariantId>> assigned;   // priority descending (mapping.rs:125-128)
+    std::vector<TaskId> prefills;         // ComputeTasks entries with variant = None, sent BEFORE the assigned ones (mapping.rs:264-275)
+    std::vector<TaskId> retracts;         // one RetractTasks message, sent first (mapping.rs:257-262)
 };
 struct WorkerTaskMapping {                // mapping.rs:16-21
     std::map<WorkerId, WorkerTaskUpdate> workers;
@@ -110,6 +112,17 @@ public:
     WorkerTaskMapping run_scheduling(uint64_t now_ms = 0);
     void on_task_finished(TaskId task);
 
+    // SchedulerConfig::proactive_filling_reserve / _max (scheduler/state.rs:14-21).  tako's defaults are 16 / 40; this
+    // class starts with proactive filling OFF (max = 0) and the embedding server switches it on.
+    void set_scheduler_config(uint32_t proactive_filling_reserve, uint32_t proactive_filling_max);
+    // reactor.rs:263-345 (RunningPrefilled): the worker started one of its prefilled tasks with the given variant
+    void on_task_running_prefilled(TaskId task, ResourceVariantId variant);
+    // on_retract_response (reactor.rs:452-498): tasks the worker gave back; returns the ComputeTasks lists for the
+    // redirect targets (target worker -> [(task, variant)])
+    std::map<WorkerId, std::vector<std::pair<TaskId, ResourceVariantId>>> on_retract_response(WorkerId worker, const std::vector<TaskId>& tasks);
+    size_t n_prefilled(WorkerId id) const;
+    const std::map<uint64_t, std::pair<WorkerId, ResourceVariantId>>& redirects() const { return redirects_; }   // SchedulerState::redirects
+
     size_t n_workers() const { return workers_.size(); }
     const std::vector<ResourceAmount>& free_resources(WorkerId id) const;   // SingleNodeTaskAssignment::free_resources
     const std::string& last_error() const { return last_error_; }
@@ -129,6 +142,8 @@ private:
         int64_t worker = -1;              // TaskRuntimeState::Assigned{worker_id, rv_id} (task.rs:22-43)
         ResourceVariantId variant = 0;
         bool live = false;
+        int64_t prefilled_on = -1;        // TaskRuntimeState::Prefilled{worker_id}
+        int64_t retracting_from = -1;     // TaskRuntimeState::Retracting{worker_id}
     };
     void flush_classes();
     void flush_ready();
@@ -146,6 +161,8 @@ private:
     std::vector<uint32_t> forget_h_;                         // finished tasks: leave the device table at the next flush
     std::vector<uint64_t> push_p_;
     std::vector<hqs_assignment> out_;
+    uint32_t pf_max_ = 0;
+    std::map<uint64_t, std::pair<WorkerId, ResourceVariantId>> redirects_;
     std::string last_error_;
 };
 

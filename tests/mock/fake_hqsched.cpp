@@ -98,4 +98,8 @@ int hqs_tick(hqs_ctx* ctx, uint32_t W, const hqs_worker* workers, const uint64_t
     ctx->stats.ticks++;
     return HQS_OK;
 }
+// proactive filling is not modelled by the double: configuration is accepted, nothing is ever prefilled
+int hqs_prefill_config(hqs_ctx*, uint32_t, uint32_t) { return HQS_OK; }
+int hqs_prefill_state(hqs_ctx*, uint32_t, const uint8_t*) { return HQS_OK; }
+int hqs_prefill_dispose(hqs_ctx*, uint32_t) { return HQS_OK; }
 }
