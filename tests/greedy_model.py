@@ -428,7 +428,7 @@ def _with_prefill(wl: Workload, ready: np.ndarray, a: np.ndarray, levels, prefil
         pos = 0
         for w in elig:
             for t in cand[pos: pos + ps].tolist():
-                extra.append((t, w, 0, 1))
+                extra.append((t, w, 255, 1))          # variant = None
                 pf_worker[t] = w
             pos += ps
     if extra:
