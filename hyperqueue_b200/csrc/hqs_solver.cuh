@@ -12,16 +12,19 @@ constexpr long long SPIN_TIMEOUT_CYCLES = 2000000000ll;   // ~1 s: a stuck grid 
 
 // Amounts come in two widths.  u64: the ABI's fixed-point fractions as they are.  u32 ("narrow"): the same
 // amounts divided by the per-resource gcd of all requested amounts — fit counts are unchanged by that
-// (floor(n / d) == floor(floor(n / g) / (d / g)) when g divides d), the quotient estimate needs one int->float
-// conversion and one fix-up instead of a 64-bit sequence, and the solver's sequential critical path shrinks
-// accordingly.  The narrow path is taken when every scaled amount of the tick is below 2^31.
+// (floor(n / d) == floor(floor(n / g) / (d / g)) when g divides d), a quotient is four integer instructions (division
+// by an invariant amount, see fit_count) instead of a 64-bit sequence, and the solver's sequential critical path
+// shrinks accordingly.  The narrow path is taken when every scaled amount of the tick is below 2^31.
 template <int RT, typename AT = u64>
 struct VarT {
     AT amount[RT];
-    float rcpf[2 * RT];  // [0, RT): fp32 1.0 / amount (0 where unused); [RT, 2 RT): fp32 of the exact amount
+    float rcpf[2 * RT];  // [0, RT): u64 amounts: fp32 1.0 / amount (0 where unused); u32 amounts: the BITS of the division
+                         // magic (see fit_count); [RT, 2 RT): fp32 of the exact amount
     u64 min_time_ms;
     u32 all_mask;
     u32 used_mask;
+    u32 shw[(RT + 3) / 4];   // u32 amounts: one byte per resource, sh1 | sh2 << 1 of the division by the invariant amount
+    u32 pad_[((RT + 3) / 4) & 1];
 };
 template <int RT, typename AT = u64>
 struct ClassT {
@@ -118,54 +121,30 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], u32 untouched, con
     return cnt;
 }
 
-// Narrow amounts (< 2^31): one conversion, one multiply and a single +1 fix-up per resource.  The host stores
-// rcpf = (1 / amount) * (1 - 2^-21): with every rounding counted the estimate is then never above the true
-// quotient and, for quotients below 2^20, less than one below it, so floor(estimate) is q or q - 1.
+// Narrow amounts (< 2^31): exact division by the invariant amount with a precomputed magic number (Granlund &
+// Montgomery, "Division by Invariant Integers using Multiplication", fig. 4.1): for 1 <= d < 2^32, l = ceil(log2 d),
+// m = floor(2^32 (2^l - d) / d) + 1, sh1 = min(l, 1), sh2 = max(l - 1, 0):  n / d = (t + ((n - t) >> sh1)) >> sh2 with
+// t = umulhi(m, n), for every 0 <= n < 2^32.  Four integer instructions per requested resource, no fix-up, no slow path.
+// The request is the same for every lane of a solver step, so the `used` tests are warp-uniform branches.
 template <int RT>
 __device__ __forceinline__ u64 fit_count(const u32 (&fr)[RT], u32 untouched, const VarT<RT, u32>& dv, u64 cap64) {
-    const u32 cap = (u32)cap64;
-    u32 cnt = cap;
-    bool big = false;
+    u32 cnt = (u32)cap64;
     const u32 used = dv.used_mask, allm = dv.all_mask;
-    if (allm == 0) {
-        // no `All` entry (the usual case): an unused resource has amount 0, which "fits cap" by itself
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const u32 n = fr[r], d = dv.amount[r];
-            const bool unconstrained = (u64)d * cap <= (u64)n || n == 0xFFFFFFFFu;
-            const float qf = __uint2float_rn(n) * dv.rcpf[r];
-            u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
-            q += (n - q * d >= d) ? 1u : 0u;
-            big |= !unconstrained && qf >= 1048576.0f;
-            cnt = unconstrained ? cnt : (cnt < q ? cnt : q);
+    for (int r = 0; r < RT; ++r) {
+        if (!((used >> r) & 1)) continue;
+        u32 q;
+        if ((allm >> r) & 1) {
+            q = (untouched >> r) & 1;
+        } else {
+            const u32 n = fr[r];
+            const u32 m = __float_as_uint(dv.rcpf[r]);
+            const u32 s = (dv.shw[r >> 2] >> ((r & 3) * 8)) & 0xFFu;
+            const u32 t = __umulhi(m, n);
+            q = (t + ((n - t) >> (s & 1u))) >> (s >> 1);
+            q = n == 0xFFFFFFFFu ? 0xFFFFFFFFu : q;                  // unbounded free amount
         }
-    } else {
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const bool on = (used >> r) & 1, all = (allm >> r) & 1;
-            const u32 n = fr[r], d = dv.amount[r];
-            const bool fits_cap = (u64)d * cap <= (u64)n;
-            const float qf = __uint2float_rn(n) * dv.rcpf[r];
-            u32 q = __float2uint_rz(fminf(qf, 1048576.0f));
-            q += (n - q * d >= d) ? 1u : 0u;
-            const u32 q_all = (untouched >> r) & 1;
-            const bool unconstrained = !on || (!all && (n == 0xFFFFFFFFu || fits_cap));
-            big |= on && !all && !unconstrained && qf >= 1048576.0f;
-            const u32 qr = all ? q_all : q;
-            cnt = unconstrained ? cnt : (cnt < qr ? cnt : qr);
-        }
-    }
-    if (big) {                                  // rare: exact divisions
-        cnt = cap;
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            if (!((used >> r) & 1)) continue;
-            u32 q;
-            if ((allm >> r) & 1) q = (untouched >> r) & 1;
-            else if (fr[r] != 0xFFFFFFFFu) q = fr[r] / dv.amount[r];
-            else continue;
-            cnt = cnt < q ? cnt : q;
-        }
+        cnt = cnt < q ? cnt : q;
     }
     return cnt;
 }

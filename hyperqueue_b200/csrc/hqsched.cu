@@ -804,7 +804,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
     if (n_classes > HQS_MAX_CLASSES) return fail(ctx, HQS_E_LIMIT, "n_classes=%u > %u", n_classes, HQS_MAX_CLASSES);
     // device layout: ClassT<RT>[Q] with RT = 4 / 8 / 16 resource slots, built as raw bytes
     const u32 RT = ctx->RT;
-    const size_t var_bytes = (size_t)RT * 16 + 16, cls_bytes = ctx->class_bytes;
+    const size_t var_bytes = RT == 4 ? sizeof(VarT<4>) : RT == 8 ? sizeof(VarT<8>) : sizeof(VarT<16>), cls_bytes = ctx->class_bytes;
     std::vector<unsigned char> blob((size_t)n_classes * cls_bytes, 0);
     for (u32 c = 0; c < n_classes; ++c) {
         const hqs_class& sc = classes[c];
@@ -856,7 +856,7 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
                 if (!((classes[c].variants[v].all_mask >> r) & 1) && classes[c].variants[v].amount[r])
                     gs[r] = std::gcd(gs[r], (u64)classes[c].variants[v].amount[r]);
     bool narrow_ok = true;
-    const size_t var_bytes32 = (size_t)RT * 12 + 16, cls_bytes32 = ctx->class_bytes32;
+    const size_t var_bytes32 = RT == 4 ? sizeof(VarT<4, u32>) : RT == 8 ? sizeof(VarT<8, u32>) : sizeof(VarT<16, u32>), cls_bytes32 = ctx->class_bytes32;
     std::vector<unsigned char> blob32((size_t)n_classes * cls_bytes32, 0);
     for (u32 r = 0; r < HQS_MAX_RESOURCES; ++r) {
         if (gs[r] == 0) gs[r] = 1;
@@ -873,13 +873,24 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
             float* rcp = reinterpret_cast<float*>(vb + (size_t)RT * 4);
             u64* min_time = reinterpret_cast<u64*>(vb + (size_t)RT * 12);
             u32* masks = reinterpret_cast<u32*>(vb + (size_t)RT * 12 + 8);
+            unsigned char* shb = vb + (size_t)RT * 12 + 16;                 // VarT::shw, one byte per resource
             u32 used = 0;
             for (u32 r = 0; r < ctx->R; ++r) {
                 const bool all = (sc.variants[v].all_mask >> r) & 1;
                 const u64 amt = all ? 0 : sc.variants[v].amount[r] / gs[r];
                 if (amt > NARROW_LIMIT) narrow_ok = false;
                 amount[r] = (u32)amt;
-                rcp[r] = amt ? (1.0f / (float)(u32)amt) * (1.0f - 4.76837158203125e-7f) : 0.0f;   // biased low by 2^-21, see fit_count
+                if (amt && amt <= NARROW_LIMIT) {
+                    // division by the invariant amount (see fit_count): magic number and the two shifts
+                    u32 l = 0;
+                    while (l < 32 && ((u64)1 << l) < amt) ++l;
+                    const u64 mm = (((u64)1 << 32) * (((u64)1 << l) - amt)) / amt + 1;
+                    const u32 magic = (u32)mm;
+                    memcpy(&rcp[r], &magic, 4);
+                    shb[r] = (unsigned char)((l < 1 ? l : 1) | ((l > 0 ? l - 1 : 0) << 1));
+                } else {
+                    rcp[r] = 0.0f;
+                }
                 rcp[RT + r] = all ? 0.0f : (float)(double)sc.variants[v].amount[r];
                 if (all || sc.variants[v].amount[r]) used |= 1u << r;
             }
