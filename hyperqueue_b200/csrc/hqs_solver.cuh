@@ -124,27 +124,24 @@ __device__ __forceinline__ u64 fit_count(const u64 (&fr)[RT], u32 untouched, con
 // Narrow amounts (< 2^31): exact division by the invariant amount with a precomputed magic number (Granlund &
 // Montgomery, "Division by Invariant Integers using Multiplication", fig. 4.1): for 1 <= d < 2^32, l = ceil(log2 d),
 // m = floor(2^32 (2^l - d) / d) + 1, sh1 = min(l, 1), sh2 = max(l - 1, 0):  n / d = (t + ((n - t) >> sh1)) >> sh2 with
-// t = umulhi(m, n), for every 0 <= n < 2^32.  Four integer instructions per requested resource, no fix-up, no slow path.
-// The request is the same for every lane of a solver step, so the `used` tests are warp-uniform branches.
+// t = umulhi(m, n), for every 0 <= n < 2^32.  A handful of integer instructions per resource, no fix-up, no slow path.
 template <int RT>
 __device__ __forceinline__ u64 fit_count(const u32 (&fr)[RT], u32 untouched, const VarT<RT, u32>& dv, u64 cap64) {
     u32 cnt = (u32)cap64;
     const u32 used = dv.used_mask, allm = dv.all_mask;
+    // straight-line: the RT quotient chains are independent (ILP on the solver's critical path); an unused resource has
+    // amount 0, magic 0, shifts 0 and is dropped by the final select
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-        if (!((used >> r) & 1)) continue;
-        u32 q;
-        if ((allm >> r) & 1) {
-            q = (untouched >> r) & 1;
-        } else {
-            const u32 n = fr[r];
-            const u32 m = __float_as_uint(dv.rcpf[r]);
-            const u32 s = (dv.shw[r >> 2] >> ((r & 3) * 8)) & 0xFFu;
-            const u32 t = __umulhi(m, n);
-            q = (t + ((n - t) >> (s & 1u))) >> (s >> 1);
-            q = n == 0xFFFFFFFFu ? 0xFFFFFFFFu : q;                  // unbounded free amount
-        }
-        cnt = cnt < q ? cnt : q;
+        const bool on = (used >> r) & 1, all = (allm >> r) & 1;
+        const u32 n = fr[r];
+        const u32 m = __float_as_uint(dv.rcpf[r]);
+        const u32 s = (dv.shw[r >> 2] >> ((r & 3) * 8)) & 0xFFu;
+        const u32 t = __umulhi(m, n);
+        u32 q = (t + ((n - t) >> (s & 1u))) >> (s >> 1);
+        q = n == 0xFFFFFFFFu ? 0xFFFFFFFFu : q;                      // unbounded free amount
+        q = all ? ((untouched >> r) & 1u) : q;
+        cnt = on ? (cnt < q ? cnt : q) : cnt;
     }
     return cnt;
 }
