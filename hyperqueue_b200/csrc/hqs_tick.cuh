@@ -1014,6 +1014,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         }
     } else {
         const u32 lt_mask = (1u << lane) - 1;
+        const bool resv_on = s_partial != 0;        // some worker is partly occupied at tick start: reservations are possible
         for (u32 pass = 0;; ++pass) {
             u32 seg_base = 0, out_base = 0;
             bool packed = (a.flags & TF_PACK) == 0;
@@ -1144,7 +1145,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 }
 #pragma unroll
                                 for (int r = 0; r < RT; ++r) fr[r] = w < W ? s_fr[(size_t)w * RT + r] : 0;
-                                lane_excl = w < W && s_excl[w] != 0;              // reserved for a waiting class
+                                lane_excl = resv_on && w < W && s_excl[w] != 0;   // reserved for a waiting class
                                 cur_tile = tile;
                                 dirty = false;
                             }
@@ -1189,7 +1190,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w; }
                             }
                             take_from<RT, AT>(fr, dv, take);                       // take == 0 leaves the lane as it is
-                            if (take) s_touch[w] = 1;
+                            if (resv_on && take) s_touch[w] = 1;
                             dirty |= tkm != 0;
                             seg_cur += __popc(tkm);
                             if (front) {
@@ -1201,7 +1202,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         }
                         if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
                         if (c_n == c) front_n = f;                               // the same class again (next level)
-                        if (remaining && s_partial && !s_noresv[c]) {
+                        if (resv_on && remaining && !s_noresv[c]) {
                             // the class is left with unplaced tasks: reservations.  The tile in registers goes back first
                             // and is loaded again afterwards (with the new exclusions)
                             if (dirty) {
@@ -1413,7 +1414,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             __syncwarp();
                         }
                     }
-                    if (remaining && s_partial && !s_noresv[c]) reserve_for(c, n_all, remaining);
+                    if (resv_on && remaining && !s_noresv[c]) reserve_for(c, n_all, remaining);
                     const u32 k = n_all - remaining;
                     if (s_kk && lane == 0) s_kk[e] = k;
                     // local share of the k assigned tasks (sharded mode: ranks are ordered by handle range)

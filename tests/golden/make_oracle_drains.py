@@ -41,10 +41,9 @@ CASES = {
     # BASELINE-sized worker pool (256 workers, Q = 16): the oracle needs minutes per case and is time-capped in most
     # ticks; the GPU suite always runs them (against the recorded specification makespan), the CPU twin only with
     # HQS_BIG_DRAINS=1
-    "w256_indep_100000_256_16_51": ("indep", [100000, 256, 16, 51], {}),
-    "w256_indep3_100000_256_16_53": ("indep", [100000, 256, 16, 53], {"variants3": True}),
-    "w256_indep3b_100000_256_16_55": ("indep", [100000, 256, 16, 55], {"variants3": True, "blocked_density": 0.05}),
-    "w256_dag_50000_256_16_57": ("dag", [50000, 256, 16, 57], {"window": 4096}),
+    "w256_indep_60000_256_8_51": ("indep", [60000, 256, 8, 51], {"n_priorities": 3}),
+    "w256_indep3b_40000_256_6_55": ("indep", [40000, 256, 6, 55], {"variants3": True, "blocked_density": 0.05, "n_priorities": 3}),
+    "w256_dag_50000_256_8_57": ("dag", [50000, 256, 8, 57], {"window": 4096}),
 }
 
 out = {}

@@ -94,7 +94,12 @@ def oracle_drain(wl: Workload, max_ticks: int = 100000, disable_prefill: bool = 
     remaining = wl.n_tasks
     per_tick = []
     while remaining > 0 and len(per_tick) < max_ticks:
-        ts, ws, vs, _ = oracle_tick(core, **(solver_opts or {}))
+        opts = dict(solver_opts or {})
+        ts, ws, vs, _ = oracle_tick(core, **opts)
+        while ts.size == 0 and opts.get("time_limit") and opts["time_limit"] < 300:
+            # HiGHS found no incumbent inside the cap (large pools): the same tick again with twice the time
+            opts["time_limit"] *= 2
+            ts, ws, vs, _ = oracle_tick(core, **opts)
         if ts.size == 0:
             raise RuntimeError(f"oracle drain stalled with {remaining} tasks left")
         for t, w in zip(ts.tolist(), ws.tolist()):
@@ -191,5 +196,10 @@ def smoke_check() -> None:
     cap = free_before.sum(0).astype(np.float64)
     u_gpu, u_ref = (used_gpu / cap).max(), (used_ref / cap).max()
     assert u_gpu >= 0.9 * u_ref, (u_gpu, u_ref, m.n_assigned(), ts.size)
-    print(f"smoke: gpu {m.n_assigned()} tasks (bottleneck utilisation {u_gpu:.3f}), oracle {ts.size} tasks ({u_ref:.3f})")
+    # ... and the resource-weighted work of the tick (sum over resources of used / capacity: what the reference's
+    # objective adds up, solver.rs:520-549) within 15 % of the oracle's, so that the per-tick task MIX is bounded too
+    w_gpu, w_ref = float((used_gpu / cap).sum()), float((used_ref / cap).sum())
+    assert w_gpu >= 0.85 * w_ref, (w_gpu, w_ref)
+    print(f"smoke: gpu {m.n_assigned()} tasks (bottleneck utilisation {u_gpu:.3f}, resource-weighted work {w_gpu:.3f}), "
+          f"oracle {ts.size} tasks ({u_ref:.3f}, {w_ref:.3f})")
     s.close()
