@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "hqs_shard_count", "hqs_shard_solve_emit", "hqs_device_result", "hqs_ready_rearm", "hqs_stream", "hqs_sync",
     "hqs_get_stats", "hqs_set_stream", "hqs_set_profile", "hqs_get_kernel_ms", "hqs_debug_read", "hqs_levels_add", "hqs_query",
     "hqs_shard_xbuf", "hqs_ipc_open", "hqs_shard_attach", "hqs_shard_tick_launch", "hqs_tick_reserve",
-    "hqs_prefill_config", "hqs_prefill_state", "hqs_prefill_dispose",
+    "hqs_prefill_config", "hqs_prefill_state", "hqs_prefill_dispose", "hqs_ready_push_range",
 ]
 HQS_IPC_HANDLE_BYTES = 64
 
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     lib.hqs_classes_set.argtypes = [vp, u32, C.POINTER(hqs_class)]
     lib.hqs_ready_push.argtypes = [vp, u32, u32p, u32p, u64p]
     lib.hqs_ready_remove.argtypes = [vp, u32, u32p]
+    lib.hqs_ready_push_range.argtypes = [vp, u32, u32, u32p, u64p]
     lib.hqs_dag_load.argtypes = [vp, u32, u32p, u64p, u32p, u32p, u32p]
     lib.hqs_tasks_finished.argtypes = [vp, u32, u32p, C.POINTER(C.c_uint32)]
     lib.hqs_tick.argtypes = [vp, u32, vp, u64p, u64p, u8p, u32, vp, C.POINTER(C.c_uint32), u64p]

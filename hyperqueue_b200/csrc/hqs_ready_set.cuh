@@ -51,13 +51,23 @@ __device__ __forceinline__ u32 find_level(const u64* __restrict__ levels, u32 n_
 }
 
 // ready-set maintenance ---------------------------------------------------------------------------
-__global__ void push_k(u32 n, const u32* __restrict__ task, const u32* __restrict__ cls,
+// class ids of a push are validated on the device, in the same stream, BEFORE push_k touches the table: flag[1] != 0 makes
+// push_k a no-op, so a rejected batch leaves the ready set unchanged (no host pass over the arrays, no host sync in between)
+__global__ void push_validate_k(u32 n, const u32* __restrict__ cls, u32 n_classes, u32* __restrict__ flag) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && cls[i] >= n_classes;
+    if (__ballot_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMax(&flag[1], 1u);
+}
+
+// task == nullptr: the handles are first_handle .. first_handle + n - 1 (a task array: no handle array crosses PCIe)
+__global__ void push_k(u32 n, const u32* __restrict__ task, u32 first_handle, const u32* __restrict__ cls,
                        const u64* __restrict__ prio_in, u32* __restrict__ key, u64* __restrict__ prio,
                        const u64* __restrict__ levels, u32 n_levels, int coarse, u32* __restrict__ newcnt,
                        u64* __restrict__ newprio) {
+    if (newcnt[1]) return;                  // push_validate_k rejected the batch
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
-    const u32 h = live ? task[i] : 0u;
+    const u32 h = live ? (task ? task[i] : first_handle + i) : 0u;
     const u64 p = live ? prio_in[i] : 0ull;
     u32 lvl = (live && n_levels) ? find_level(levels, n_levels, p, coarse != 0) : ~0u;
     // unknown priority: report it to the host (one atomic per warp), key it provisionally to level 0;

@@ -737,7 +737,7 @@ int hqs_create(hqs_ctx** out, int device, uint32_t n_resources, uint32_t flags) 
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newcnt, sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newcnt, 2 * sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_newprio, NEWPRIO_CAP * sizeof(u64));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(u32));
     {
@@ -925,11 +925,9 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes) 
     return HQS_OK;
 }
 
-int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
-                   const uint64_t* priority) {
-    if (!ctx) return HQS_E_INVALID;
-    if (n == 0) return HQS_OK;
-    if (!task || !class_id || !priority) return fail(ctx, HQS_E_INVALID, "null task arrays");
+namespace {
+// shared body of hqs_ready_push / hqs_ready_push_range (task == nullptr: handles first_handle .. first_handle + n - 1)
+int push_impl(hqs_ctx* ctx, u32 n, const u32* task, u32 first_handle, const u32* class_id, const u64* priority) {
     if (ctx->Q == 0) return fail(ctx, HQS_E_STATE, "hqs_classes_set has not been called");
     if (ctx->dag) return fail(ctx, HQS_E_STATE, "hqs_ready_push is not available after hqs_dag_load");
     CU(cudaSetDevice(ctx->device));
@@ -941,29 +939,36 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
         CU(cudaMalloc(&ctx->d_push_cls, (size_t)ctx->push_cap * 4));
         CU(cudaMalloc(&ctx->d_push_prio, (size_t)ctx->push_cap * 8));
     }
-    CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (task) CU(cudaMemcpyAsync(ctx->d_push_task, task, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_push_cls, class_id, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_push_prio, priority, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    // validate on the host while the staging copies are in flight (they touch no scheduler state)
-    u32 max_h = 0, max_c = 0;
-    max_of_u32_pair(task, class_id, n, &max_h, &max_c);
-    if (max_c >= ctx->Q || max_h == ~0u) {
+    // the table must hold the largest handle before the kernel runs: a host pass over the handle array while the staging
+    // copies are in flight (a range push knows it); class ids are validated on the device (push_validate_k)
+    u32 max_h = first_handle + (n - 1);
+    if (task) {
+        u32 dummy = 0;
+        max_of_u32_pair(task, task, n, &max_h, &dummy);
+    } else if (max_h < first_handle) {
+        max_h = ~0u;                                                  // the range wraps around
+    }
+    if (max_h == ~0u) {
         cudaStreamSynchronize(ctx->stream);      // the caller may free its arrays as soon as we return
-        if (max_c >= ctx->Q) return fail(ctx, HQS_E_INVALID, "class id %u >= n_classes %u", max_c, ctx->Q);
         return fail(ctx, HQS_E_INVALID, "task handle 0xFFFFFFFF is reserved");
     }
     int rc = ensure_handles(ctx, max_h + 1);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    CU(cudaMemsetAsync(ctx->d_newcnt, 0, 2 * sizeof(u32), ctx->stream));
+    push_validate_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_cls, ctx->Q, ctx->d_newcnt);
+    push_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, task ? ctx->d_push_task : nullptr, first_handle, ctx->d_push_cls,
+                                                     ctx->d_push_prio, ctx->d_key, ctx->d_prio, ctx->d_levels,
+                                                     (u32)ctx->dev_levels.size(), ctx->coarse ? 1 : 0, ctx->d_newcnt, ctx->d_newprio);
+    ctx->stats.kernel_launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_small, ctx->d_newcnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_small[1]) return fail(ctx, HQS_E_INVALID, "a class id of the batch is >= n_classes %u (nothing was pushed)", ctx->Q);
     ctx->n_handles = std::max(ctx->n_handles, max_h + 1);
     ctx->stats.n_handles = ctx->n_handles;
-    CU(cudaMemsetAsync(ctx->d_newcnt, 0, sizeof(u32), ctx->stream));
-    push_k<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->d_push_task, ctx->d_push_cls, ctx->d_push_prio, ctx->d_key,
-                                                     ctx->d_prio, ctx->d_levels, (u32)ctx->dev_levels.size(),
-                                                     ctx->coarse ? 1 : 0, ctx->d_newcnt, ctx->d_newprio);
-    ctx->stats.kernel_launches++;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_small, ctx->d_newcnt, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     const u32 newcnt = ctx->h_small[0];
     if (newcnt) {
         std::vector<u64> fresh;
@@ -982,6 +987,22 @@ int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_
         if ((rc = relevel_all(ctx))) return rc;
     }
     return HQS_OK;
+}
+}  // namespace
+
+int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
+                   const uint64_t* priority) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n == 0) return HQS_OK;
+    if (!task || !class_id || !priority) return fail(ctx, HQS_E_INVALID, "null task arrays");
+    return push_impl(ctx, n, task, 0, class_id, priority);
+}
+
+int hqs_ready_push_range(hqs_ctx* ctx, uint32_t first_task, uint32_t n, const uint32_t* class_id, const uint64_t* priority) {
+    if (!ctx) return HQS_E_INVALID;
+    if (n == 0) return HQS_OK;
+    if (!class_id || !priority) return fail(ctx, HQS_E_INVALID, "null task arrays");
+    return push_impl(ctx, n, nullptr, first_task, class_id, priority);
 }
 
 int hqs_levels_add(hqs_ctx* ctx, uint32_t n, const uint64_t* priority) {

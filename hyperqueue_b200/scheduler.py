@@ -249,7 +249,11 @@ class GpuScheduler:
         self._grow_tasks(int(h.max()) + 1)
         self._task_class[h] = c
         self._task_prio[h] = p
-        self._check(self._lib.hqs_ready_push(self._ctx, h.size, L.ptr(h), L.ptr(c), L.ptr(p)))
+        if h.size > 1 and int(h[-1]) - int(h[0]) == h.size - 1 and (np.diff(h.astype(np.int64)) == 1).all():
+            # a task array: consecutive handles, no handle array crosses PCIe
+            self._check(self._lib.hqs_ready_push_range(self._ctx, int(h[0]), h.size, L.ptr(c), L.ptr(p)))
+        else:
+            self._check(self._lib.hqs_ready_push(self._ctx, h.size, L.ptr(h), L.ptr(c), L.ptr(p)))
 
     def remove_ready_tasks(self, handles) -> None:
         h = np.ascontiguousarray(handles, dtype=np.uint32)

@@ -134,6 +134,10 @@ int hqs_classes_set(hqs_ctx* ctx, uint32_t n_classes, const hqs_class* classes);
  * class and priority.  Handles may be new or re-used after the task left the ready set. */
 int hqs_ready_push(hqs_ctx* ctx, uint32_t n, const uint32_t* task, const uint32_t* class_id,
                    const uint64_t* priority);
+/* The same for a task array: the handles are first_task .. first_task + n - 1 (tako's job arrays are consecutive
+ * TaskIds, so the shim's handles are too) and no handle array crosses PCIe.  A batch with an invalid class id is
+ * rejected as a whole (validated on the device before the table is touched). */
+int hqs_ready_push_range(hqs_ctx* ctx, uint32_t first_task, uint32_t n, const uint32_t* class_id, const uint64_t* priority);
 /* Declares priority values before any task carries them.  Needed when the ready set is sharded over
  * several contexts (every rank must number the priority levels identically).  A context whose levels were declared
  * does not prune them on its own (the ranks would diverge). */
