@@ -1104,144 +1104,150 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     }
                 }
                 if (plain && (packed || skip_sat) && !level_packed) {
-                    // ---- lean first-fit over ALL remaining groups (no more packing can happen): the frontier tile's free
-                    //      vectors stay in registers (lane = worker) from group to group, the next group's request is
-                    //      prefetched, and the only work on the group-to-group dependency chain is fit -> ballot -> take.
-                    u32 cur_tile = 0xFFFFFFFFu;
-                    bool dirty = false, lane_excl = false;
-                    AT fr[RT];
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) fr[r] = 0;
-                    uint2 ge_n = s_glist[li];
-                    u32 c_n = s_gcl[li] & 0xFFFFu;
-                    Var dv_n = classes[c_n].v[0];
-                    u32 front_n = s_front[c_n];
-                    for (u32 e = li; e < n_list; ++e) {
-                        const uint2 ge = ge_n;
-                        const u32 c = c_n;
-                        Var dv = dv_n;
-                        dv.all_mask = 0;                                         // plain tick: lets the compiler drop the `All` arm
-                        const u32 tile0 = front_n;
-                        if (e + 1 < n_list) {
-                            ge_n = s_glist[e + 1];
-                            c_n = s_gcl[e + 1] & 0xFFFFu;
-                            dv_n = classes[c_n].v[0];
-                            front_n = s_front[c_n];
-                        }
-                        const u32 g = ge.x, n_all = ge.y;
-                        u32 remaining = n_all, tile = tile0, f = tile0;
-                        const u32 seg_lo = seg_base;
-                        u32 seg_cur = seg_base;
-                        bool front = true;
-                        while (remaining && tile < n_tiles) {
-                            const u32 w = tile * 32 + lane;
-                            if (tile != cur_tile) {
+                    // two instantiations of the same loop: without reservations and proactive filling (no worker is partly
+                    // occupied at tick start, the usual M1 / zero-duration case) the bookkeeping for them is compiled out
+                    auto lean_loop = [&](auto extras_tag) {
+                        constexpr bool EXTRAS = decltype(extras_tag)::value;
+                        // ---- lean first-fit over ALL remaining groups (no more packing can happen): the frontier tile's free
+                        //      vectors stay in registers (lane = worker) from group to group, the next group's request is
+                        //      prefetched, and the only work on the group-to-group dependency chain is fit -> ballot -> take.
+                        u32 cur_tile = 0xFFFFFFFFu;
+                        bool dirty = false, lane_excl = false;
+                        AT fr[RT];
+    #pragma unroll
+                        for (int r = 0; r < RT; ++r) fr[r] = 0;
+                        uint2 ge_n = s_glist[li];
+                        u32 c_n = s_gcl[li] & 0xFFFFu;
+                        Var dv_n = classes[c_n].v[0];
+                        u32 front_n = s_front[c_n];
+                        for (u32 e = li; e < n_list; ++e) {
+                            const uint2 ge = ge_n;
+                            const u32 c = c_n;
+                            Var dv = dv_n;
+                            dv.all_mask = 0;                                         // plain tick: lets the compiler drop the `All` arm
+                            const u32 tile0 = front_n;
+                            if (e + 1 < n_list) {
+                                ge_n = s_glist[e + 1];
+                                c_n = s_gcl[e + 1] & 0xFFFFu;
+                                dv_n = classes[c_n].v[0];
+                                front_n = s_front[c_n];
+                            }
+                            const u32 g = ge.x, n_all = ge.y;
+                            u32 remaining = n_all, tile = tile0, f = tile0;
+                            const u32 seg_lo = seg_base;
+                            u32 seg_cur = seg_base;
+                            bool front = true;
+                            while (remaining && tile < n_tiles) {
+                                const u32 w = tile * 32 + lane;
+                                if (tile != cur_tile) {
+                                    if (dirty) {
+                                        const u32 wo = cur_tile * 32 + lane;
+                                        if (wo < W) {
+    #pragma unroll
+                                            for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
+                                        }
+                                    }
+    #pragma unroll
+                                    for (int r = 0; r < RT; ++r) fr[r] = w < W ? s_fr[(size_t)w * RT + r] : 0;
+                                    lane_excl = EXTRAS && resv_on && w < W && s_excl[w] != 0;   // reserved for a waiting class
+                                    cur_tile = tile;
+                                    dirty = false;
+                                }
+                                ++n_visits;
+                                const u64 cnt = lane_excl ? 0 : fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
+                                const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
+                                u32 take = 0, exc = 0, handed = 0;
+                                if (hasm) {
+                                    const u32 first = (u32)__ffs(hasm) - 1;
+                                    const u32 fall = __shfl_sync(0xffffffffu, cnt >= remaining ? 1u : 0u, first);
+                                    if (fall) {
+                                        take = lane == first ? remaining : 0;
+                                        handed = remaining;
+                                    } else if (remaining <= 0x03FFFFFFu) {
+                                        u32 inc = (u32)cnt;
+    #pragma unroll
+                                        for (int d = 1; d < 32; d <<= 1) {
+                                            const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                            if ((int)lane >= d) inc += y;
+                                        }
+                                        exc = inc - (u32)cnt;
+                                        if (cnt && exc < remaining) take = min((u32)cnt, remaining - exc);
+                                        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+                                        handed = min(total, remaining);
+                                    } else {
+                                        u64 inc = cnt;
+    #pragma unroll
+                                        for (int d = 1; d < 32; d <<= 1) {
+                                            const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
+                                            if ((int)lane >= d) inc += y;
+                                        }
+                                        const u64 e64 = inc - cnt;
+                                        exc = (u32)(e64 < remaining ? e64 : remaining);
+                                        if (cnt && e64 < remaining) take = (u32)(cnt < remaining - e64 ? cnt : remaining - e64);
+                                        const u64 total = __shfl_sync(0xffffffffu, inc, 31);
+                                        handed = (u32)(total < remaining ? total : remaining);
+                                    }
+                                }
+                                const u32 tkm = __ballot_sync(0xffffffffu, take != 0);
+                                if (take) {
+                                    const u32 si = seg_cur + __popc(tkm & lt_mask);
+                                    if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w; }
+                                }
+                                take_from<RT, AT>(fr, dv, take);                       // take == 0 leaves the lane as it is
+                                if (EXTRAS && resv_on && take) s_touch[w] = 1;
+                                dirty |= tkm != 0;
+                                seg_cur += __popc(tkm);
+                                if (front) {
+                                    const u32 alive = __ballot_sync(0xffffffffu, !(cnt < remaining && take == (u32)cnt));
+                                    if (alive == 0) f = tile + 1; else front = false;
+                                }
+                                remaining -= handed;
+                                if (remaining) ++tile;
+                            }
+                            if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
+                            if (c_n == c) front_n = f;                               // the same class again (next level)
+                            if (EXTRAS && resv_on && remaining && !s_noresv[c]) {
+                                // the class is left with unplaced tasks: reservations.  The tile in registers goes back first
+                                // and is loaded again afterwards (with the new exclusions)
                                 if (dirty) {
                                     const u32 wo = cur_tile * 32 + lane;
                                     if (wo < W) {
-#pragma unroll
+    #pragma unroll
                                         for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
                                     }
+                                    dirty = false;
                                 }
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) fr[r] = w < W ? s_fr[(size_t)w * RT + r] : 0;
-                                lane_excl = resv_on && w < W && s_excl[w] != 0;   // reserved for a waiting class
-                                cur_tile = tile;
-                                dirty = false;
+                                __syncwarp();
+                                reserve_for(c, n_all, remaining);
+                                cur_tile = 0xFFFFFFFFu;
                             }
-                            ++n_visits;
-                            const u64 cnt = lane_excl ? 0 : fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
-                            const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
-                            u32 take = 0, exc = 0, handed = 0;
-                            if (hasm) {
-                                const u32 first = (u32)__ffs(hasm) - 1;
-                                const u32 fall = __shfl_sync(0xffffffffu, cnt >= remaining ? 1u : 0u, first);
-                                if (fall) {
-                                    take = lane == first ? remaining : 0;
-                                    handed = remaining;
-                                } else if (remaining <= 0x03FFFFFFu) {
-                                    u32 inc = (u32)cnt;
-#pragma unroll
-                                    for (int d = 1; d < 32; d <<= 1) {
-                                        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
-                                        if ((int)lane >= d) inc += y;
-                                    }
-                                    exc = inc - (u32)cnt;
-                                    if (cnt && exc < remaining) take = min((u32)cnt, remaining - exc);
-                                    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
-                                    handed = min(total, remaining);
-                                } else {
-                                    u64 inc = cnt;
-#pragma unroll
-                                    for (int d = 1; d < 32; d <<= 1) {
-                                        const u64 y = __shfl_up_sync(0xffffffffu, inc, d);
-                                        if ((int)lane >= d) inc += y;
-                                    }
-                                    const u64 e64 = inc - cnt;
-                                    exc = (u32)(e64 < remaining ? e64 : remaining);
-                                    if (cnt && e64 < remaining) take = (u32)(cnt < remaining - e64 ? cnt : remaining - e64);
-                                    const u64 total = __shfl_sync(0xffffffffu, inc, 31);
-                                    handed = (u32)(total < remaining ? total : remaining);
-                                }
+                            const u32 k = n_all - remaining;
+                            if (EXTRAS && s_kk && lane == 0) s_kk[e] = k;
+                            u32 k_loc = k;
+                            if (before) {
+                                const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
+                                const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
+                                k_loc = k > bef ? k - bef : 0;
+                                k_loc = k_loc < loc ? k_loc : loc;
                             }
-                            const u32 tkm = __ballot_sync(0xffffffffu, take != 0);
-                            if (take) {
-                                const u32 si = seg_cur + __popc(tkm & lt_mask);
-                                if (si < SEG_CAP) { a.seg_cum[si] = (n_all - remaining) + exc + take; a.seg_wv[si] = w; }
+                            if (lane == 0) {
+                                GroupOut go;
+                                go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_cur - seg_lo;
+                                a.gout[g] = go;
                             }
-                            take_from<RT, AT>(fr, dv, take);                       // take == 0 leaves the lane as it is
-                            if (resv_on && take) s_touch[w] = 1;
-                            dirty |= tkm != 0;
-                            seg_cur += __popc(tkm);
-                            if (front) {
-                                const u32 alive = __ballot_sync(0xffffffffu, !(cnt < remaining && take == (u32)cnt));
-                                if (alive == 0) f = tile + 1; else front = false;
+                            out_base += k_loc;
+                            seg_base = seg_cur;
+                            if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+                        }
+                        if (dirty) {
+                            const u32 wo = cur_tile * 32 + lane;
+                            if (wo < W) {
+    #pragma unroll
+                                for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
                             }
-                            remaining -= handed;
-                            if (remaining) ++tile;
                         }
-                        if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
-                        if (c_n == c) front_n = f;                               // the same class again (next level)
-                        if (resv_on && remaining && !s_noresv[c]) {
-                            // the class is left with unplaced tasks: reservations.  The tile in registers goes back first
-                            // and is loaded again afterwards (with the new exclusions)
-                            if (dirty) {
-                                const u32 wo = cur_tile * 32 + lane;
-                                if (wo < W) {
-#pragma unroll
-                                    for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
-                                }
-                                dirty = false;
-                            }
-                            __syncwarp();
-                            reserve_for(c, n_all, remaining);
-                            cur_tile = 0xFFFFFFFFu;
-                        }
-                        const u32 k = n_all - remaining;
-                        if (s_kk && lane == 0) s_kk[e] = k;
-                        u32 k_loc = k;
-                        if (before) {
-                            const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
-                            const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
-                            k_loc = k > bef ? k - bef : 0;
-                            k_loc = k_loc < loc ? k_loc : loc;
-                        }
-                        if (lane == 0) {
-                            GroupOut go;
-                            go.k = k; go.out_off = out_base; go.seg_lo = seg_lo; go.seg_n = seg_cur - seg_lo;
-                            a.gout[g] = go;
-                        }
-                        out_base += k_loc;
-                        seg_base = seg_cur;
-                        if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
-                    }
-                    if (dirty) {
-                        const u32 wo = cur_tile * 32 + lane;
-                        if (wo < W) {
-#pragma unroll
-                            for (int r = 0; r < RT; ++r) s_fr[(size_t)wo * RT + r] = fr[r];
-                        }
-                    }
+                    };
+                    if (resv_on || s_kk) lean_loop(std::true_type{}); else lean_loop(std::false_type{});
                     __syncwarp();
                     n_fast += n_list - li;
                     li = n_list;

@@ -31,6 +31,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
