@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 src = os.path.join(ROOT, "gpurun_out")
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
@@ -29,10 +29,11 @@ if os.path.exists(lp):
             agg.setdefault(r[ki].split("(")[0].replace("<unnamed>::", ""), []).append(float(r[vi].replace(",", "")) / 1000.0)
         except ValueError:
             pass
-    tick = {k: v for k, v in agg.items() if any(x in k for x in ("count_k", "solve_k", "emit_k"))}
+    tick = {k: v for k, v in agg.items() if any(x in k for x in ("tick_k", "count_k", "solve_k", "emit_k"))}
     tot = sum(sum(v) / len(v) for v in tick.values())
     out += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `HQS_DEBUG_NO_COOP=1` so that",
-            "ncu sees the otherwise cooperative solver launch)", "", "| kernel | launches | avg us | share of the tick |", "|---|---|---|---|"]
+            "ncu's kernel replay sees the otherwise cooperative tick kernel; cold cache, serialised: compare SHARES)", "",
+            "| kernel | launches | avg us | share of the tick |", "|---|---|---|---|"]
     for k, v in agg.items():
         share = f"{100 * (sum(v) / len(v)) / tot:.1f} %" if k in tick else "(maintenance)"
         out.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.1f} | {share} |")
@@ -66,7 +67,7 @@ if os.path.exists(rp):
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
         unit = units[hdr.index("dram__bytes_read.sum")]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-        metrics[name.split("<")[0]] = {"dram_bytes_read": rd * scale if rd is not None else None,
+        metrics[name.split("<")[0].strip()] = {"dram_bytes_read": rd * scale if rd is not None else None,
                                        "dram_bytes_write": (wr or 0) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(units[hdr.index("dram__bytes_write.sum")], 1),
                                        "duration_us": val("gpu__time_duration.sum")}
     out.append("")
@@ -79,6 +80,6 @@ if os.path.exists(bp):
     json.dump(d, open(os.path.join(dst, f"{tag}_bench.json"), "w"), indent=1)
     out += ["## bench.py (not under a profiler)", "", "```", json.dumps({k: d[k] for k in ("value", "unit", "ms_per_step", "gpu_launches", "clocks")}),
             "kernels: " + json.dumps(d.get("kernels")), "roofline: " + json.dumps(d.get("roofline")), "e2e: " + json.dumps(d.get("e2e")),
-            "drain_m2: " + json.dumps(d.get("drain_m2")), "cpu_baseline: " + json.dumps(d.get("cpu_baseline")), "```", ""]
+            "cpu_baseline: " + json.dumps(d.get("cpu_baseline")), "extra: " + json.dumps(d.get("extra")), "```", ""]
 open(os.path.join(dst, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
