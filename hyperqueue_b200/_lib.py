@@ -10,7 +10,7 @@ HQS_MAX_RESOURCES = 16
 HQS_MAX_VARIANTS = 8
 HQS_MAX_WORKERS = 1024
 HQS_MAX_CLASSES = 4096
-HQS_MAX_GROUPS = 4096
+HQS_MAX_GROUPS = 8192
 HQS_AMOUNT_MAX = (1 << 64) - 1
 HQS_TIME_INF = (1 << 64) - 1
 HQS_CREATE_NO_PACK, HQS_CREATE_WIDE_AMOUNTS, HQS_CREATE_SHARE_DEVICE = 1, 2, 4

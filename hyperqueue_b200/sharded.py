@@ -131,6 +131,7 @@ class ShardedScheduler:
             n = C.c_uint32(0)
             s._check(s._lib.hqs_tick_fetch(s._ctx, cap, L.ptr(out), C.byref(n), L.ptr(free_after)))
             a = out[: n.value].copy()
+            self._record(a)
             a["task"] += np.uint32(self.lo)
             s.free = free_after
             return a, free_after
@@ -147,6 +148,42 @@ class ShardedScheduler:
         n = C.c_uint32(0)
         s._check(s._lib.hqs_tick_fetch(s._ctx, cap, L.ptr(out), C.byref(n), L.ptr(free_after)))
         a = out[: n.value].copy()
+        self._record(a)
         a["task"] += np.uint32(self.lo)
         s.free = free_after
         return a, free_after
+
+    def _record(self, a_local) -> None:
+        """TaskRuntimeState::Assigned{worker_id, rv_id} of this rank's tasks (local handles), as GpuScheduler.run_scheduling
+        keeps it: needed to return the resources when the tasks finish."""
+        if a_local.size:
+            self.s._task_worker[a_local["task"]] = a_local["worker"]
+            self.s._task_variant[a_local["task"]] = a_local["variant"]
+
+    def tasks_finished(self, handles) -> None:
+        """task_finished for GLOBAL handles, called with the same list on every rank: every rank holds the replicated free
+        vectors, but only the owner of a task knows where it ran, so the per-worker amounts to give back are summed over the
+        ranks (one all-reduce of a [W][R] matrix, or nothing with world == 1)."""
+        s = self.s
+        h = np.asarray(handles, dtype=np.int64)
+        mine = h[(h >= self.lo) & (h < self.hi)] - self.lo
+        add = np.zeros_like(s.free)
+        reset = np.zeros(s.free.shape, dtype=bool)
+        if mine.size:
+            wi, cl, va = s._task_worker[mine], s._task_class[mine], s._task_variant[mine]
+            assert (wi >= 0).all(), "a finished task of this rank was never assigned"
+            np.add.at(add, wi, s._amount_tab[cl, va])
+            allm = s._all_tab[cl, va]
+            if allm.any():
+                ws, rs = np.nonzero(allm)
+                reset[wi[ws], rs] = True
+            s._task_worker[mine] = -1
+        if self.world > 1:
+            t = torch.from_numpy(np.stack([add.astype(np.int64), reset.astype(np.int64)]))
+            dev = self.device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+            t = t.to(dev)
+            dist.all_reduce(t, group=self.group)
+            t = t.cpu().numpy()
+            add, reset = t[0].astype(np.uint64), t[1] > 0
+        s.free = s.free + add.astype(np.uint64)
+        s.free[reset] = s.total[reset]

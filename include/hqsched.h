@@ -38,7 +38,7 @@ extern "C" {
 #define HQS_MAX_VARIANTS 8u     /* variants per request class (reference allows 32, request.rs:305) */
 #define HQS_MAX_WORKERS 1024u   /* workers per tick (one solver thread per worker)                  */
 #define HQS_MAX_CLASSES 4096u   /* interned request classes (ResourceRqId)                          */
-#define HQS_MAX_GROUPS 4096u    /* (priority level x class) groups; levels are coarsened to fit     */
+#define HQS_MAX_GROUPS 8192u    /* (priority level x class) groups of LIVE levels; more: levels are merged */
 #define HQS_AMOUNT_MAX (~(uint64_t)0)
 #define HQS_TIME_INF (~(uint64_t)0)
 

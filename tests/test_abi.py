@@ -107,8 +107,11 @@ def test_solver_shared_memory_budget(lib):
     out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
     statics = [int(m) for blk in re.findall(r"Function [^\n]*tick_k[^\n]*\n[^\n]*", out) for m in re.findall(r"SHARED:(\d+)", blk)]
     assert len(statics) == 6
-    W, Q, n_pos = 1024, 4096, 4096
-    worst_mandatory = W * 16 * 8 + W * (4 + 8 + 1 + 1 + 2) + Q * 3 + n_pos * 12 + 10 * 16
-    assert max(statics) + worst_mandatory <= 227 * 1024, (max(statics), worst_mandatory)
-    # the emit step of the worker CTAs: <= 128 KB of counters + 64 KB of group records + the segment cache
-    assert max(statics) + 128 * 1024 + 64 * 1024 + 8 * 1024 <= 227 * 1024
+    # mandatory solver arrays: free amounts [W][RT], per-worker words, per-class words, the group list (12 B per entry).
+    # Largest supported corners: 1024 workers x 16 wide resource slots with 4096 list entries, and 8192 entries
+    # (HQS_MAX_GROUPS) with <= 8 resource slots; a tick beyond both fails with HQS_E_LIMIT before it is launched
+    for W, RT, at, Q, n_pos in [(1024, 16, 8, 4096, 4096), (1024, 8, 8, 4096, 8192), (1024, 16, 4, 4096, 8192)]:
+        worst_mandatory = W * RT * at + W * (4 + 8 + 1 + 1 + 2) + Q * 3 + n_pos * 12 + 10 * 16
+        assert max(statics) + worst_mandatory <= 227 * 1024, (W, RT, at, n_pos, max(statics), worst_mandatory)
+    # the emit step of the worker CTAs: <= 128 KB of counters (+ the group records when they fit) + the segment cache
+    assert max(statics) + 128 * 1024 + 8 * 1024 <= 227 * 1024

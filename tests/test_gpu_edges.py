@@ -67,8 +67,29 @@ def test_large_class_table_uses_global_class_path():
     assert m.n_assigned() > 100
 
 
+def test_many_live_levels_stay_exact_up_to_the_group_limit():
+    """test_many_cuts shape (test_scheduler_sn.rs:1129-1146): 3200 priority levels x 2 classes = 6400 groups fit
+    HQS_MAX_GROUPS (8192): no coarsening, the tick equals the specification and strict priority order holds."""
+    rng = np.random.default_rng(5)
+    n = 6400
+    classes = [[{"amounts": {0: 1 * FR}}], [{"amounts": {0: 2 * FR}}]]
+    total = np.full((300, 1), 8 * FR, dtype=np.uint64)
+    wl = P.Workload(1, classes, total, total.copy(), (np.arange(n) % 2).astype(np.uint32), (np.arange(n) // 2).astype(np.int32))
+    s = P.gpu_scheduler(wl)
+    fb = s.free.copy()
+    m = s.run_scheduling()
+    st = s.stats()
+    assert st["coarsened"] == 0 and st["n_levels"] == 3200
+    exp, exp_free = G.model_tick(wl, np.ones(n, dtype=bool), fb)
+    assert np.array_equal(m.assignments, exp) and np.array_equal(m.free_after, exp_free)
+    assert (np.diff(wl.task_user_priority[m.assignments["task"]]) <= 0).all()
+    cnt = np.bincount(wl.task_class[m.assignments["task"]], minlength=2)
+    assert abs(int(cnt[0]) - 800) <= 10 and abs(int(cnt[1]) - 800) <= 10      # the reference pins 800 / 800 +- 10
+    s.close()
+
+
 def test_more_groups_than_the_limit_are_coarsened():
-    wl = _random_workload(60000, 128, 300, 4, 2, seed=4, n_prio=40)      # 300 x 40 = 12000 groups > 4096
+    wl = _random_workload(60000, 128, 300, 4, 2, seed=4, n_prio=40)      # 300 x 40 = 12000 groups > 8192
     s = P.gpu_scheduler(wl)
     fb = s.free.copy()
     m = s.run_scheduling()

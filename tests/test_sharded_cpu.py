@@ -132,3 +132,52 @@ def test_peer_handle_exchange_plumbing():
         assert opened == [bytes((other * 37 + i) % 256 for i in range(64))]
         assert attached[0] == world and attached[1] == rank
         assert attached[2][rank] == 0x1000 + rank and attached[2][other] == 0x2000 + (other * 37) % 256
+
+
+class _FakeMirror:
+    """The host-side fields of GpuScheduler that ShardedScheduler.tasks_finished touches (no device)."""
+
+    def __init__(self, n_local, W, R):
+        self._task_worker = np.full(n_local, -1, dtype=np.int64)
+        self._task_class = np.zeros(n_local, dtype=np.uint32)
+        self._task_variant = np.zeros(n_local, dtype=np.uint8)
+        self._amount_tab = np.zeros((2, 8, R), dtype=np.uint64)
+        self._amount_tab[0, 0] = [10000, 0]
+        self._amount_tab[1, 0] = [20000, 5000]
+        self._all_tab = np.zeros((2, 8, R), dtype=bool)
+        self.total = np.full((W, R), 80000, dtype=np.uint64)
+        self.free = self.total.copy()
+
+
+def _finished_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hyperqueue_b200.sharded import ShardedScheduler, block_range
+    n_total, W, R = 10, 3, 2
+    lo, hi = block_range(n_total, rank, world)
+    sh = ShardedScheduler.__new__(ShardedScheduler)
+    sh.s, sh.rank, sh.world, sh.group, sh.lo, sh.hi, sh.device = _FakeMirror(hi - lo, W, R), rank, world, None, lo, hi, torch.device("cpu")
+    # the replicated solve placed global task t of class t % 2 on worker t % 3: every rank saw the same free vectors
+    for t in range(n_total):
+        amount = sh.s._amount_tab[t % 2, 0]
+        sh.s.free[t % 3] -= amount
+    a = np.zeros(hi - lo, dtype=[("task", "<u4"), ("worker", "<u2"), ("variant", "u1"), ("kind", "u1")])
+    a["task"] = np.arange(hi - lo); a["worker"] = (np.arange(lo, hi) % 3)
+    sh.s._task_class[:] = np.arange(lo, hi) % 2
+    sh._record(a)
+    sh.tasks_finished(np.arange(n_total))          # the same global list on every rank
+    ret[rank] = sh.s.free.tobytes()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_tasks_finished_returns_resources_on_every_rank():
+    """Each rank knows where ITS tasks ran; the amounts to give back are summed over the ranks, so the replicated free
+    vectors stay identical and return to the totals."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_finished_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    total = np.full((3, 2), 80000, dtype=np.uint64)
+    for rank in range(world):
+        assert np.array_equal(np.frombuffer(ret[rank], dtype=np.uint64).reshape(3, 2), total)
