@@ -44,6 +44,7 @@ CASES = {
     "w256_indep_60000_256_8_51": ("indep", [60000, 256, 8, 51], {"n_priorities": 3}),
     "w256_indep3b_40000_256_6_55": ("indep", [40000, 256, 6, 55], {"variants3": True, "blocked_density": 0.05, "n_priorities": 3}),
     "w256_dag_50000_256_8_57": ("dag", [50000, 256, 8, 57], {"window": 4096}),
+    "w256_indep_100000_256_16_51": ("indep", [100000, 256, 16, 51], {}),           # Q = 16, 8 levels: hours of HiGHS time
 }
 
 out = {}
