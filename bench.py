@@ -275,6 +275,14 @@ def run_cuda(args) -> dict:
         s._sh = (allc, before)
         s._check(lib.hqs_shard_solve_emit(s._ctx, C.c_void_p(allc.data_ptr()), C.c_void_p(before.data_ptr()), n_tasks))
 
+    if world > 1:
+        # one local (unsharded) tick per rank first: module load and first-launch costs differ between processes by
+        # hundreds of milliseconds, and a sharded tick waits for its peers on the device
+        warm = P.gpu_scheduler(make_workload({"tasks_per_gpu": 4096, "workers": n_workers}, seed=1), device=local_rank)
+        warm.run_scheduling()
+        warm.close()
+        barrier_host = dist.barrier
+        barrier_host()
     if p2p:
         from hyperqueue_b200.sharded import gather_peer_handles, open_and_attach
         ok = 1

@@ -9,6 +9,7 @@ constexpr u32 PACK_MAX_ITER = 64;
 constexpr u32 PACK_CHUNK_DIV = 8;
 constexpr u32 HQS_MAX_PEERS = 16;      // ranks of a sharded ready set
 constexpr long long SPIN_TIMEOUT_CYCLES = 2000000000ll;   // ~1 s: a stuck grid must not hang the GPU
+constexpr long long PEER_TIMEOUT_CYCLES = 30000000000ll;  // ~15 s: another PROCESS may be late by a first-launch module load or an allocation
 
 // Amounts come in two widths.  u64: the ABI's fixed-point fractions as they are.  u32 ("narrow"): the same
 // amounts divided by the per-resource gcd of all requested amounts — fit counts are unchanged by that

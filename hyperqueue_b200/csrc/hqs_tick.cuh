@@ -368,8 +368,9 @@ __device__ void worker_cta(const TickArgs& a, unsigned char* smem) {
             u32 cmd = 0;
             if (ok) {
                 const long long t0 = clock64();
+                const long long limit = a.x_world ? PEER_TIMEOUT_CYCLES + SPIN_TIMEOUT_CYCLES : SPIN_TIMEOUT_CYCLES;
                 while ((cmd = ld_acquire(&a.sync->cmd)) == seen) {
-                    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { cmd = 0; break; }
+                    if (clock64() - t0 > limit) { cmd = 0; break; }
                     __nanosleep(100);
                 }
             }
@@ -586,7 +587,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             const u32* myflags = a.x_peer[a.x_rank] + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
             const long long t0 = clock64();
             while (ld_acquire_sys(myflags + tid) != a.x_seq) {
-                if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) { s_err = 2; break; }
+                if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { s_err = 2; break; }
                 __nanosleep(32);
             }
         }
