@@ -49,9 +49,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 N_CLASSES = 16
 FREE_SCALE = 1024
 METRIC = "assignments/sec on 1M ready tasks x 256 workers x 4 resource kinds"
-CFG2 = {"name": "cfg2-M1", "tasks_per_gpu": 1_000_000, "workers": 256,
+CFG2 = {"name": "cfg2-M1", "tasks_per_gpu": 1_000_000, "workers": 256, "free_scale": 1024,
         "workload": "cfg2-M1: 1M independent tasks, 256 workers, R=4 (gpus fractional), Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"}
-CFG5 = {"name": "cfg5-M1", "tasks_per_gpu": 1_250_000, "workers": 1024,
+# free_scale 4096: mode M1 needs capacity >= demand for the WHOLE job; with 1024 x the per-worker numbers the 10 M tasks of
+# 8 GPUs ask for 89 % of the pool's gpus and first-fit leaves tasks behind (measured: all_assigned false, 34 k segments)
+CFG5 = {"name": "cfg5-M1", "tasks_per_gpu": 1_250_000, "workers": 1024, "free_scale": 4096,
         "workload": "cfg5-M1: 1.25M independent tasks per GPU (10M at 8 GPUs) block-sharded by handle, 1024 workers, R=4 (gpus fractional), "
                     "Q=16 Zipf(1.1), 8 priorities, one tick, all assignable"}
 BYTES_CONTRACT = 36      # V*R*4 amounts + 8 priority + 4 class/flags read, 8 written per assignment (cfg2, cfg5)
@@ -102,15 +104,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_workload(cfg: dict, seed: int, n_classes: int = N_CLASSES, free_scale: int = FREE_SCALE, **kw):
+def make_workload(cfg: dict, seed: int, n_classes: int = N_CLASSES, free_scale=None, **kw):
     import workloads as WL          # synthetic inputs only; does not import the oracle
-    return WL.make_independent(cfg["tasks_per_gpu"], cfg["workers"], n_classes, seed=seed, free_scale=free_scale, **kw)
+    fs = cfg.get("free_scale", FREE_SCALE) if free_scale is None else free_scale
+    return WL.make_independent(cfg["tasks_per_gpu"], cfg["workers"], n_classes, seed=seed, free_scale=fs, **kw)
 
 
 def config_block(cfg: dict, world: int, **extra) -> dict:
     """The `config` object of the JSON line: identical keys and values in the CUDA arm and in the reference arm."""
     c = {"workload": cfg["workload"], "name": cfg["name"], "tasks_per_gpu": cfg["tasks_per_gpu"], "workers": cfg["workers"],
-         "classes": N_CLASSES, "pool_free_scale": FREE_SCALE}
+         "classes": N_CLASSES, "pool_free_scale": cfg.get("free_scale", FREE_SCALE)}
     c.update(extra)
     return c
 
