@@ -30,7 +30,7 @@ struct TickHeaderOut {
     u32 n_segments;
     u32 error;       // 1 = segment overflow, 2 = a grid wait timed out, 3 = out_cap too small (nothing was emitted)
     u32 n_prefilled; // prefill records (kind 1) behind the assignments
-    u32 pad;
+    u32 pad;         // detail of error 2: which wait timed out
     unsigned long long dbg[8];   // clock64 phase lengths of the solver CTA (hqs_debug_read)
 };
 

@@ -563,7 +563,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
 
     // ---- prologue B: wait for the histogram; sharded: exchange the count vectors over NVLink
     if (a.flags & TF_COUNT) {
-        if (tid == 0 && !spin_until_ge(&a.sync->count_done, nW)) s_err = 2;
+        if (tid == 0 && !spin_until_ge(&a.sync->count_done, nW)) s_err = 21;        // the histogram never completed
     }
     __syncthreads();
     const long long t_counted = clock64();
@@ -587,7 +587,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             const u32* myflags = a.x_peer[a.x_rank] + (size_t)2 * HQS_MAX_PEERS * HQS_MAX_GROUPS + (size_t)parity * HQS_MAX_PEERS;
             const long long t0 = clock64();
             while (ld_acquire_sys(myflags + tid) != a.x_seq) {
-                if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { s_err = 2; break; }
+                if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { s_err = 22 + (tid << 8); break; }       // peer `tid` never sent its counts
                 __nanosleep(32);
             }
         }
@@ -858,7 +858,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             const u32 np = s_npacks + 1;
             s_npacks = np;
             st_release(&a.sync->cmd, (np << 2) | CMD_PACK);
-            if (!spin_until_ge(&a.sync->pack_done, np * nW)) s_err = 2;
+            if (!spin_until_ge(&a.sync->pack_done, np * nW)) s_err = 23;
         }
         bar_named(2, TICK_THREADS);
         // c. the workers filled themselves: take their free vectors back
@@ -1513,7 +1513,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             }
     }
     if (tid == 0) {
-        if (!spin_until_ge(&a.sync->emit_done, nW)) s_err = 2;
+        if (!spin_until_ge(&a.sync->emit_done, nW)) s_err = 24;
     }
     __syncthreads();
     const long long t_end = clock64();
@@ -1528,7 +1528,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         h.n_segments = n_segments;
         h.error = err;
         h.n_prefilled = s_npref;
-        h.pad = 0;
+        h.pad = s_err ? s_err : (werr ? 25u : 0u);       // which wait timed out (21 histogram, 22 | peer << 8, 23 pack, 24 emit, 25 a worker CTA)
         h.dbg[0] = (unsigned long long)(t_counted - t_start);     // staging + wait for the histogram
         h.dbg[1] = (unsigned long long)(t_prologue - t_counted);  // exchange + compaction + demand
         h.dbg[2] = (unsigned long long)(t_solved - t_prologue);   // the solver warp

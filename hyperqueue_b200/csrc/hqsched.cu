@@ -698,7 +698,13 @@ int wait_header(hqs_ctx* ctx, TickHeaderOut* hdr) {
         }
     }
     if (hdr->error) ctx->sync_dirty = true;
-    if (hdr->error == 2) return fail(ctx, HQS_E_CUDA, "a grid synchronisation of the tick kernel timed out");
+    if (hdr->error == 2) {
+        const u32 d = hdr->pad & 0xFFu, peer = hdr->pad >> 8;
+        return fail(ctx, HQS_E_CUDA, "a grid synchronisation of the tick kernel timed out (%s%s%u; stage %llu, exchange+compact %llu cycles)",
+                    d == 21 ? "the histogram of the worker CTAs" : d == 22 ? "count vector of peer rank " : d == 23 ? "the pack step" :
+                    d == 24 ? "the emit step" : "a worker CTA waiting for the solver", d == 22 ? "" : ", code ", d == 22 ? peer : d,
+                    (unsigned long long)hdr->dbg[0], (unsigned long long)hdr->dbg[1]);
+    }
     if (hdr->error == 1) return fail(ctx, HQS_E_LIMIT, "count-segment overflow (> %u segments in one tick)", SEG_CAP);
     return HQS_OK;
 }
