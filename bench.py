@@ -314,6 +314,10 @@ def run_cuda(args) -> dict:
             launch(s)
 
     def barrier():
+        # the device drains FIRST: a sharded tick is a cooperative kernel that occupies every SM and waits for its peers on
+        # the device; an NCCL kernel that slips in between two ticks on one rank (and cannot start on the other, whose SMs
+        # are all taken by a tick waiting for exactly that rank) would dead-lock until the tick's peer time-out
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
