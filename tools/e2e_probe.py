@@ -12,12 +12,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import hyperqueue_b200._lib as L
 from workloads import gpu_scheduler
-from bench import make_workload
+from bench import CFG2, make_workload
 from hyperqueue_b200 import priority_from_user
 
 lib = L.load_library()
 N, W = 1_000_000, 256
-wl = make_workload(N, seed=0)
+wl = make_workload(CFG2, seed=0)
 s = gpu_scheduler(wl, add_tasks=False)
 s._sync_classes()
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
@@ -53,7 +53,7 @@ print("host max over 2 x 1M u32: %.3f ms" % t(lambda: (handles.max(), cls.max())
 
 
 def push():
-    rc = lib.hqs_ready_push(s._ctx, N, L.ptr(handles), L.ptr(cls), L.ptr(prio))
+    rc = lib.hqs_ready_push_range(s._ctx, 0, N, L.ptr(cls), L.ptr(prio))       # a task array: no handle array over PCIe
     assert rc == 0
 
 
@@ -74,5 +74,5 @@ tt = []
 for _ in range(10):
     t0 = time.perf_counter(); push(); t1 = time.perf_counter(); tick(); t2 = time.perf_counter()
     tp.append(t1 - t0); tt.append(t2 - t1)
-print("hqs_ready_push: %.3f ms   hqs_tick: %.3f ms   sum %.3f ms" % (np.median(tp) * 1e3, np.median(tt) * 1e3,
+print("hqs_ready_push_range: %.3f ms   hqs_tick: %.3f ms   sum %.3f ms" % (np.median(tp) * 1e3, np.median(tt) * 1e3,
                                                                      (np.median(tp) + np.median(tt)) * 1e3))
