@@ -103,8 +103,9 @@ def test_tick_out_cap_overflow_is_an_error_without_partial_results():
     s.close()
 
 
-def test_many_priority_levels_are_coarsened_not_rejected():
-    """Shape of test_many_cuts (test_scheduler_sn.rs:1129-1146): 300 x 8 cpus, 3200 levels x 2 classes."""
+def test_many_priority_levels_are_exact_up_to_the_group_limit():
+    """Shape of test_many_cuts (test_scheduler_sn.rs:1129-1146): 300 x 8 cpus, 3200 levels x 2 classes = 6400 groups, inside
+    HQS_MAX_GROUPS (8192): no coarsening (round 1 merged levels at 4096 groups)."""
     classes = [[{"amounts": {0: 1 * FR}}], [{"amounts": {0: 2 * FR}}]]
     total = np.full((300, 1), 8 * FR, dtype=np.uint64)
     cls = np.tile(np.array([0, 1], dtype=np.uint32), 3200)
@@ -115,7 +116,9 @@ def test_many_priority_levels_are_coarsened_not_rejected():
     assert P.judge_tick(wl, wl.worker_free, m.assignments).ok
     c = np.bincount(wl.task_class[m.assignments["task"]], minlength=2)
     assert abs(int(c[0]) - int(c[1])) < 10 and abs(int(c[0]) - 800) < 10, c
-    assert s.stats()["coarsened"] == 1
+    assert s.stats()["coarsened"] == 0
+    exp, _ = G.model_tick(wl, np.ones(wl.n_tasks, dtype=bool), wl.worker_free)
+    assert np.array_equal(m.assignments, exp)
     s.close()
 
 
