@@ -134,7 +134,7 @@ def test_drain_makespan_vs_oracle(key):
     earlier is fine).  Six cases were used while designing the packing rules, eight (see make_oracle_drains.py)
     were generated afterwards as held-out checks."""
     golden = json.load(open(GOLDEN))[key]
-    wl = (P.make_dag if key.startswith("dag") else P.make_independent)(*golden["args"], **golden.get("kwargs", {}))
+    wl = (P.make_dag if "dag" in key.split("_")[:2] else P.make_independent)(*golden["args"], **golden.get("kwargs", {}))
     ticks, per_tick = P.gpu_drain(wl)
     assert sum(per_tick) == wl.n_tasks
     if key.startswith("w256_"):
