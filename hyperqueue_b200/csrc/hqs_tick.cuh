@@ -26,7 +26,7 @@ constexpr u32 EMIT_ROWS_MAX = 16;     // rows of 32 tasks per emit warp and chun
 constexpr u32 EMIT_SEG_SMEM = 1024;   // count segments cached in shared memory by the emit step
 constexpr u32 CMD_PACK = 1, CMD_EMIT = 2, CMD_EXIT = 3;      // grid commands: cmd word = (sequence << 2) | type
 constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3, BLK_PREFILL = 4;    // block commands inside the solver CTA
-constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4;
+constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4, TF_NO_REFRESH = 8;   // TF_NO_REFRESH: measuring aid (HQS_DEBUG_NO_REFRESH)
 constexpr u32 SM_NONE = 0xFFFFFFFFu;
 constexpr u32 PF_SEG_CAP = 1u << 18;  // prefill segments (eligible workers summed over classes) per tick
 constexpr u32 MU_MAX_PASSES = 8;      // restarts of the min-utilisation rule before the remaining violators are dropped
@@ -181,24 +181,14 @@ __device__ void count_chunk(const TickArgs& a, u32 b, u32* s_hist) {
 //                group g starts; second pass: running counter.
 // HBM traffic: 4 B read per table slot (L2 hit: the count step read it microseconds ago), 8 B written per
 // assignment, 4 B key write-back per assignment.
-__device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut* s_go, const u32* s_segc, const u32* s_segw,
-                           bool seg_smem, const u32* before, u32 n_assigned) {
+// Two halves: emit_prepare needs the task table and the scanned chunk table only — a worker CTA with a single chunk
+// runs it WHILE the solver CTA solves and keeps its rows in registers; emit_finish needs the solver's group records.
+struct EmitRows { u32 kk[EMIT_ROWS_MAX], peers[EMIT_ROWS_MAX]; };
+
+__device__ __forceinline__ void emit_prepare(const TickArgs& a, u32 b, u32* s_cnt, EmitRows& er) {
     const u32 G = a.G, Q = a.Q, nwarps = a.emit_warps, rows = a.rows;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // A chunk holds an assigned task only if, for some group, fewer than k[g] tasks of the group precede
-    // the chunk (the assigned ones are the first k[g] in handle order): in a drain tick only the first
-    // chunks qualify, the rest leave after reading one table row.
     const u32* row = a.table + (size_t)b * G;
-    {
-        bool mine = false;
-        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
-            const u32 bef = before ? __ldcg(before + g) : 0u;
-            u32 k = a.g_smem ? s_go[g].k : __ldcg(&a.gout[g].k);
-            if (a.pf_shift) { const u32 kpf = __ldcg(&a.gout2[g].x); k = k > kpf ? k : kpf; }      // the prefill range lies behind the assigned ranks
-            mine |= __ldcg(row + g) + bef < k;
-        }
-        if (!__syncthreads_or(mine)) return;
-    }
     for (u32 i = threadIdx.x; i < nwarps * G; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
     const u32 base = b * a.chunk;
@@ -206,22 +196,21 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
     const bool active = warp < nwarps;
     const u32 wbeg = base + warp * (32 * rows);
     u32* mycnt = s_cnt + (active ? warp : 0) * G;
-    u32 kk[EMIT_ROWS_MAX], peers[EMIT_ROWS_MAX];
 #pragma unroll
     for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
         const u32 i = wbeg + j * 32 + lane;
-        kk[j] = (active && j < (int)rows && i < end) ? a.key[i] : 0u;
+        er.kk[j] = (active && j < (int)rows && i < end) ? a.key[i] : 0u;
     }
 #pragma unroll
     for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
-        peers[j] = 0;
+        er.peers[j] = 0;
         if (active && j < (int)rows) {                       // warp-uniform
-            const bool ready = (kk[j] & KEY_READY) != 0;
-            const u32 g = ((key_level(kk[j]) * Q + key_class(kk[j])) << a.pf_shift) | ((kk[j] >> 28) & a.pf_shift);
+            const bool ready = (er.kk[j] & KEY_READY) != 0;
+            const u32 g = ((key_level(er.kk[j]) * Q + key_class(er.kk[j])) << a.pf_shift) | ((er.kk[j] >> 28) & a.pf_shift);
             const u32 act = __ballot_sync(0xffffffffu, ready);
             u32 pm = same_key_lanes(act, g, a.nbits);
             if (!ready) pm = 0;
-            peers[j] = pm;
+            er.peers[j] = pm;
             // pass 1: per-warp counts (rows in order; the leader of each key adds its lanes)
             if (ready && (u32)(__ffs(pm) - 1) == lane) mycnt[g] += __popc(pm);
             __syncwarp();
@@ -238,12 +227,38 @@ __device__ void emit_chunk(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut*
         }
     }
     __syncthreads();
+}
+
+// A chunk holds an assigned task only if, for some group, fewer than k[g] tasks of the group precede the chunk (the
+// assigned ones are the first k[g] in handle order): in a drain tick only the first chunks qualify, the rest leave
+// after reading one table row.
+__device__ __forceinline__ bool emit_chunk_has_work(const TickArgs& a, u32 b, const GroupOut* s_go, const u32* before) {
+    const u32 G = a.G;
+    const u32* row = a.table + (size_t)b * G;
+    bool mine = false;
+    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+        const u32 bef = before ? __ldcg(before + g) : 0u;
+        u32 k = a.g_smem ? s_go[g].k : __ldcg(&a.gout[g].k);
+        if (a.pf_shift) { const u32 kpf = __ldcg(&a.gout2[g].x); k = k > kpf ? k : kpf; }      // the prefill range lies behind the assigned ranks
+        mine |= __ldcg(row + g) + bef < k;
+    }
+    return __syncthreads_or(mine) != 0;
+}
+
+__device__ __forceinline__ void emit_finish(const TickArgs& a, u32 b, u32* s_cnt, const GroupOut* s_go, const u32* s_segc, const u32* s_segw,
+                                            bool seg_smem, const u32* before, u32 n_assigned, const EmitRows& er) {
+    const u32 G = a.G, Q = a.Q, nwarps = a.emit_warps, rows = a.rows;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 base = b * a.chunk;
+    const bool active = warp < nwarps;
+    const u32 wbeg = base + warp * (32 * rows);
+    u32* mycnt = s_cnt + (active ? warp : 0) * G;
     // pass 2: rank and emit
 #pragma unroll
     for (int j = 0; j < (int)EMIT_ROWS_MAX; ++j) {
         if (active && j < (int)rows) {                       // warp-uniform
             const u32 i = wbeg + j * 32 + lane;
-            const u32 k = kk[j], pm = peers[j];
+            const u32 k = er.kk[j], pm = er.peers[j];
             const u32 g = ((key_level(k) * Q + key_class(k)) << a.pf_shift) | ((k >> 28) & a.pf_shift);
             if (pm) {
                 const u32 leader = __ffs(pm) - 1;
@@ -361,9 +376,19 @@ __device__ void worker_cta(const TickArgs& a, unsigned char* smem) {
         __threadfence();
         atomicAdd(&a.sync->scan_done, 1u);
     }
+    // ---- first half of emit, while the solver CTA solves: a CTA that owns a single chunk ranks its ready tasks now and
+    //      keeps the rows in registers (a pack command in between reuses the shared memory: then emit starts over)
+    EmitRows er;
+    bool prepared = false;
+    if (ok && (a.flags & TF_EMIT) && me < a.P && a.P <= nW) {
+        if (threadIdx.x == 0) s_ok = spin_until_ge(&a.sync->scan_done, nW) ? 1u : 0u;
+        __syncthreads();
+        prepared = s_ok != 0;
+        __syncthreads();
+        if (prepared) emit_prepare(a, me, s_u32, er);
+    }
     // ---- command loop
-    u32 seen = 0;
-    for (;;) {
+    auto next_cmd = [&](u32 seen) -> u32 {
         if (threadIdx.x == 0) {
             u32 cmd = 0;
             if (ok) {
@@ -380,48 +405,68 @@ __device__ void worker_cta(const TickArgs& a, unsigned char* smem) {
         __syncthreads();
         const u32 cmd = s_cmd;
         __syncthreads();
-        seen = cmd;
-        const u32 type = cmd & 3u;
-        if (type == CMD_PACK) {
-            PackArgs p;
-            p.pk = a.pk; p.total_rw = a.total_rw; p.rem_time = a.rem_time; p.blocked = a.blocked;
-            p.excluded = a.min_util ? a.excl_glob : nullptr; p.classes64 = a.classes64; p.W = a.W; p.Q = a.Q; p.R = a.R;
-            pack_body<RT>(p, smem);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) atomicAdd(&a.sync->pack_done, 1u);
-            continue;
-        }
-        if (type == CMD_EMIT) {
-            if (threadIdx.x == 0) s_ok = spin_until_ge(&a.sync->scan_done, nW) ? 1u : 0u;
-            __syncthreads();
-            if (s_ok) {
-                const u32 G = a.G;
-                u32* s_cnt = s_u32;                                                      // [emit_warps][G]
-                GroupOut* s_go = reinterpret_cast<GroupOut*>(s_u32 + a.emit_warps * G);    // [G] when g_smem
-                u32* s_segc = reinterpret_cast<u32*>(s_go + (a.g_smem ? G : 0));          // [EMIT_SEG_SMEM]
-                u32* s_segw = s_segc + EMIT_SEG_SMEM;
-                const u32 n_seg = __ldcg(&a.hdr->n_segments);
-                const bool seg_smem = n_seg <= EMIT_SEG_SMEM;
-                const u32* before = a.x_world ? a.x_before : a.before_ext;
-                if (me < a.P) {
-                    if (a.g_smem)
-                        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
-                            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(a.gout + g));
-                            GroupOut go; go.k = v.x; go.out_off = v.y; go.seg_lo = v.z; go.seg_n = v.w;
-                            s_go[g] = go;
-                        }
-                    if (seg_smem)
-                        for (u32 i = threadIdx.x; i < n_seg; i += blockDim.x) { s_segc[i] = __ldcg(a.seg_cum + i); s_segw[i] = __ldcg(a.seg_wv + i); }
-                    __syncthreads();
-                    const u32 n_assigned = __ldcg(&a.hdr->n_assigned);
-                    for (u32 b = me; b < a.P; b += nW) emit_chunk(a, b, s_cnt, s_go, s_segc, s_segw, seg_smem, before, n_assigned);
+        return cmd;
+    };
+    // emit of this CTA's chunks; rows != nullptr: chunk `me` was prepared above
+    auto do_emit = [&](EmitRows* rows) {
+        if (threadIdx.x == 0) s_ok = spin_until_ge(&a.sync->scan_done, nW) ? 1u : 0u;
+        __syncthreads();
+        if (s_ok) {
+            const u32 G = a.G;
+            u32* s_cnt = s_u32;                                                      // [emit_warps][G]
+            GroupOut* s_go = reinterpret_cast<GroupOut*>(s_u32 + a.emit_warps * G);    // [G] when g_smem
+            u32* s_segc = reinterpret_cast<u32*>(s_go + (a.g_smem ? G : 0));          // [EMIT_SEG_SMEM]
+            u32* s_segw = s_segc + EMIT_SEG_SMEM;
+            const u32 n_seg = __ldcg(&a.hdr->n_segments);
+            const bool seg_smem = n_seg <= EMIT_SEG_SMEM;
+            const u32* before = a.x_world ? a.x_before : a.before_ext;
+            if (me < a.P) {
+                if (a.g_smem)
+                    for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+                        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(a.gout + g));
+                        GroupOut go; go.k = v.x; go.out_off = v.y; go.seg_lo = v.z; go.seg_n = v.w;
+                        s_go[g] = go;
+                    }
+                if (seg_smem)
+                    for (u32 i = threadIdx.x; i < n_seg; i += blockDim.x) { s_segc[i] = __ldcg(a.seg_cum + i); s_segw[i] = __ldcg(a.seg_wv + i); }
+                __syncthreads();
+                const u32 n_assigned = __ldcg(&a.hdr->n_assigned);
+                if (rows) {
+                    if (emit_chunk_has_work(a, me, s_go, before))
+                        emit_finish(a, me, s_cnt, s_go, s_segc, s_segw, seg_smem, before, n_assigned, *rows);
+                } else {
+                    for (u32 b = me; b < a.P; b += nW) {
+                        if (!emit_chunk_has_work(a, b, s_go, before)) continue;
+                        EmitRows r2;
+                        emit_prepare(a, b, s_cnt, r2);
+                        emit_finish(a, b, s_cnt, s_go, s_segc, s_segw, seg_smem, before, n_assigned, r2);
+                    }
                 }
-            } else if (threadIdx.x == 0) {
-                atomicExch(&a.sync->error, 2u);
             }
+        } else if (threadIdx.x == 0) {
+            atomicExch(&a.sync->error, 2u);
         }
-        break;      // CMD_EMIT or CMD_EXIT
+    };
+    u32 cmd = next_cmd(0);
+    if (prepared && (cmd & 3u) == CMD_EMIT) {
+        do_emit(&er);                       // the prepared rows are used by the FIRST command only (a pack reuses the shared memory)
+    } else {
+        for (;;) {
+            const u32 type = cmd & 3u;
+            if (type == CMD_PACK) {
+                PackArgs p;
+                p.pk = a.pk; p.total_rw = a.total_rw; p.rem_time = a.rem_time; p.blocked = a.blocked;
+                p.excluded = a.min_util ? a.excl_glob : nullptr; p.classes64 = a.classes64; p.W = a.W; p.Q = a.Q; p.R = a.R;
+                pack_body<RT>(p, smem);
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) atomicAdd(&a.sync->pack_done, 1u);
+                cmd = next_cmd(cmd);
+                continue;
+            }
+            if (type == CMD_EMIT) do_emit(nullptr);
+            break;      // CMD_EMIT or CMD_EXIT
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -925,6 +970,34 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         }
         __threadfence();
         bar_named(2, TICK_THREADS);
+        // e. frontiers of the level's single-variant classes on what the pack left: the first worker that can still take
+        //    one task (one warp per group; the solver warp alone would find out tile by tile, group by group).  Hand-backs
+        //    lower the frontiers again where free amounts grow.
+        if (!(a.flags & TF_NO_REFRESH)) {
+            for (u32 gi = warp; gi < ng; gi += TICK_WARPS) {
+                const u32 c = s_gcl[li + gi] & 0xFFFFu;
+                if (classes[c].n_variants != 1) continue;
+                const Var& dv = classes[c].v[0];
+                const u32 old = s_front[c];
+                u32 res = n_tiles * 32;
+                for (u32 tile = old >> 5; tile < n_tiles; ++tile) {
+                    const u32 w = tile * 32 + lane;
+                    u64 cnt = 0;
+                    if (w < W && !s_excl[w]) {
+                        AT fr[RT];
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) fr[r] = s_fr[(size_t)w * RT + r];
+                        const uint8_t blk = blocked ? blocked[(size_t)w * Q + c] : 0;
+                        const u64 rt = a.any_time_limit ? s_remtime[w] : HQS_TIME_INF;
+                        if (admissible(dv, 0, blk, rt)) cnt = fit_count<RT>(fr, s_unt[w], dv, 1);
+                    }
+                    const u32 m = __ballot_sync(0xffffffffu, cnt != 0);
+                    if (m) { res = tile * 32 + (u32)__ffs(m) - 1; break; }
+                }
+                if (lane == 0 && res > old) s_front[c] = (unsigned short)res;
+            }
+            bar_named(2, TICK_THREADS);
+        }
     };
 
     // ---- reservations (solver.rs:133-151; specification: tests/greedy_model.py::_Tick.reserve).  A class that is left
@@ -1005,6 +1078,12 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     // the solver warp
     // =============================================================================================
     u32 n_assigned = 0, n_segments = 0, n_visits = 0, n_fast = 0;
+    long long t_pack = 0, t_general = 0;      // cycles inside pack commands / the general first-fit loop (hqs_debug_read)
+#ifdef HQS_TRACE
+    // measuring build (tools/trace_build.sh): cycle sums of the sections of the lean loop replace the phase stamps
+    u32 tr_top = 0, tr_rec = 0, tr_cyc[4] = {0, 0, 0, 0}, tr_n[4] = {0, 0, 0, 0}, tr_fit = 0, tr_load = 0;   // visit kinds: dead tile, fall, scan (tile exhausted), scan (group ends)
+#define TR_CLK() ([] { u32 c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)::"memory"); return c_; }())
+#endif
     bool seg_overflow = false;
     if (warp != 0) {
         for (;;) {
@@ -1097,8 +1176,10 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 s_blk[4] = (u32)__double2loint(phi); s_blk[5] = (u32)__double2hiint(phi);
                             }
                             __syncwarp();
+                            const long long tp0 = clock64();
                             bar_named(1, TICK_THREADS);
                             block_work(BLK_PACK);
+                            t_pack += clock64() - tp0;
                             packed = true;
                             level_packed = s_err == 0;
                         }
@@ -1122,11 +1203,14 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         Var dv_n = classes[c_n].v[0];
                         u32 front_n = s_front[c_n];
                         for (u32 e = li; e < n_list; ++e) {
+#ifdef HQS_TRACE
+                            const u32 tr0 = TR_CLK();
+#endif
                             const uint2 ge = ge_n;
                             const u32 c = c_n;
                             Var dv = dv_n;
                             dv.all_mask = 0;                                         // plain tick: lets the compiler drop the `All` arm
-                            const u32 tile0 = front_n;
+                            const u32 tile0 = front_n >> 5;                         // s_front[c]: frontier WORKER (tile-granular here)
                             if (e + 1 < n_list) {
                                 ge_n = s_glist[e + 1];
                                 c_n = s_gcl[e + 1] & 0xFFFFu;
@@ -1138,7 +1222,15 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             const u32 seg_lo = seg_base;
                             u32 seg_cur = seg_base;
                             bool front = true;
+#ifdef HQS_TRACE
+                            u32 tr1 = TR_CLK();
+                            tr_top += tr1 - tr0;
+#endif
                             while (remaining && tile < n_tiles) {
+#ifdef HQS_TRACE
+                                const u32 v0 = TR_CLK();
+                                u32 kind = 0;
+#endif
                                 const u32 w = tile * 32 + lane;
                                 if (tile != cur_tile) {
                                     if (dirty) {
@@ -1155,13 +1247,22 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                     dirty = false;
                                 }
                                 ++n_visits;
+#ifdef HQS_TRACE
+                                const u32 v1 = TR_CLK();
+#endif
                                 const u64 cnt = lane_excl ? 0 : fit_count<RT>(fr, 0u, dv, remaining);     // lanes beyond the pool hold zeros: 0
                                 const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
+#ifdef HQS_TRACE
+                                const u32 v2 = TR_CLK() + (hasm & 0);
+#endif
                                 u32 take = 0, exc = 0, handed = 0;
                                 if (hasm) {
                                     const u32 first = (u32)__ffs(hasm) - 1;
                                     const u32 fall = __shfl_sync(0xffffffffu, cnt >= remaining ? 1u : 0u, first);
                                     if (fall) {
+#ifdef HQS_TRACE
+                                        kind = 1;
+#endif
                                         take = lane == first ? remaining : 0;
                                         handed = remaining;
                                     } else if (remaining <= 0x03FFFFFFu) {
@@ -1175,6 +1276,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                         if (cnt && exc < remaining) take = min((u32)cnt, remaining - exc);
                                         const u32 total = __shfl_sync(0xffffffffu, inc, 31);
                                         handed = min(total, remaining);
+#ifdef HQS_TRACE
+                                        kind = total < remaining ? 2 : 3;
+#endif
                                     } else {
                                         u64 inc = cnt;
     #pragma unroll
@@ -1204,9 +1308,22 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                                 }
                                 remaining -= handed;
                                 if (remaining) ++tile;
+#ifdef HQS_TRACE
+                                {
+                                    const u32 v3 = TR_CLK() + (remaining & 0);
+                                    tr_load += v1 - v0; tr_fit += v2 - v1;
+                                    if (kind == 0) { tr_cyc[0] += v3 - v0; ++tr_n[0]; }
+                                    if (kind == 1) { tr_cyc[1] += v3 - v0; ++tr_n[1]; }
+                                    if (kind == 2) { tr_cyc[2] += v3 - v0; ++tr_n[2]; }
+                                    if (kind == 3) { tr_cyc[3] += v3 - v0; ++tr_n[3]; }
+                                }
+#endif
                             }
-                            if (f != tile0 && lane == 0) s_front[c] = (unsigned short)f;
-                            if (c_n == c) front_n = f;                               // the same class again (next level)
+#ifdef HQS_TRACE
+                            const u32 tr3 = TR_CLK() + (remaining & 0);
+#endif
+                            if (f != tile0 && lane == 0) s_front[c] = (unsigned short)(f * 32);
+                            if (c_n == c && f != tile0) front_n = f * 32;            // the same class again (next level)
                             if (EXTRAS && resv_on && remaining && !s_noresv[c]) {
                                 // the class is left with unplaced tasks: reservations.  The tile in registers goes back first
                                 // and is loaded again afterwards (with the new exclusions)
@@ -1239,6 +1356,9 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             out_base += k_loc;
                             seg_base = seg_cur;
                             if (seg_base > SEG_CAP) { seg_overflow = true; seg_base = SEG_CAP; }
+#ifdef HQS_TRACE
+                            tr_rec += TR_CLK() + (out_base & 0) - tr3;
+#endif
                         }
                         if (dirty) {
                             const u32 wo = cur_tile * 32 + lane;
@@ -1255,6 +1375,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     break;
                 }
                 // ---- the groups of the level, in order: first-fit (after what pack placed)
+                const long long tg0 = clock64();
                 u32 region_end = seg_base;
                 if (level_packed) {
                     region_end = seg_base + 2u * W * s_cbase[ng];
@@ -1289,7 +1410,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             }
                             // free amounts grew: no frontier may lie beyond the first tile that got something back
                             for (u32 c2 = lane; c2 < Q; c2 += 32)
-                                if (s_front[c2] > ex_lo) s_front[c2] = (unsigned short)ex_lo;
+                                if (s_front[c2] > ex_lo * 32) s_front[c2] = (unsigned short)(ex_lo * 32);
                             __syncwarp();
                         }
                     }
@@ -1299,7 +1420,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                         // variant id (specification: tests/greedy_model.py::_Tick.next_variant).
                         const bool last_round = vi + 1 == nv;
                         bool front = true;
-                        for (u32 tile = s_front[c]; tile < n_tiles && remaining; ++tile) {
+                        for (u32 tile = s_front[c] >> 5; tile < n_tiles && remaining; ++tile) {
                             ++n_visits;
                             const u32 w = tile * 32 + lane;
                             const bool in_pool = w < W;
@@ -1344,6 +1465,11 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             // ---- hand out `remaining` in worker order: the first worker that can take anything often
                             //      takes it all (mode M1); otherwise an inclusive scan over the tile
                             const u32 hasm = __ballot_sync(0xffffffffu, cnt != 0);
+                            if (hasm == 0 && nv == 1) {                  // a dead tile (one variant: nothing to record per worker)
+                                if (front && lane == 0) s_front[c] = (unsigned short)((tile + 1) * 32);
+                                __syncwarp();
+                                continue;
+                            }
                             u32 take = 0, exc = 0, handed = 0;
                             if (hasm) {
                                 const u32 first = (u32)__ffs(hasm) - 1;
@@ -1414,7 +1540,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             }
                             if (front) {
                                 const u32 alive = __ballot_sync(0xffffffffu, in_pool && !lane_dead);
-                                if (alive == 0 && last_round) { if (lane == 0) s_front[c] = (unsigned short)(tile + 1); }
+                                if (alive == 0 && last_round) { if (lane == 0) s_front[c] = (unsigned short)((tile + 1) * 32); }
                                 else front = false;
                             }
                             remaining -= handed;
@@ -1444,6 +1570,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                     }
                 }
                 if (level_packed) seg_base = region_end > SEG_CAP ? SEG_CAP : region_end;
+                t_general += clock64() - tg0;
                 li = lj;
             }
             n_assigned = out_base;
@@ -1533,10 +1660,18 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         h.dbg[1] = (unsigned long long)(t_prologue - t_counted);  // exchange + compaction + demand
         h.dbg[2] = (unsigned long long)(t_solved - t_prologue);   // the solver warp
         h.dbg[3] = (unsigned long long)(t_end - t_solved);        // emit (+ free vectors)
-        h.dbg[4] = (unsigned long long)n_list | ((unsigned long long)n_visits << 32);       // groups | tile visits
+        // groups (16 bits) | cycles / 256 inside the general first-fit loop (16 bits) | tile visits
+        h.dbg[4] = (unsigned long long)(n_list & 0xFFFFu) | ((unsigned long long)((t_general >> 8) & 0xFFFF) << 16) | ((unsigned long long)n_visits << 32);
         h.dbg[5] = (unsigned long long)(t_end - t_start);
         h.dbg[6] = global_timer_ns() - gt_start;                  // the same interval in ns
-        h.dbg[7] = (unsigned long long)s_npacks | ((unsigned long long)n_fast << 32);      // pack commands | groups of the lean loop
+        // pack commands (8 bits) | cycles / 256 inside them (24 bits) | groups of the lean loop
+        h.dbg[7] = (unsigned long long)(s_npacks & 0xFFu) | ((unsigned long long)((t_pack >> 8) & 0xFFFFFF) << 8) | ((unsigned long long)n_fast << 32);
+#ifdef HQS_TRACE
+        h.dbg[0] = ((unsigned long long)tr_rec << 32) | tr_top;
+        h.dbg[1] = ((unsigned long long)tr_fit << 32) | tr_load;
+        for (int q = 0; q < 4; ++q) h.dbg[2 + q] = ((unsigned long long)tr_n[q] << 32) | tr_cyc[q];
+        h.dbg[6] = (unsigned long long)(t_solved - t_prologue);
+#endif
         *a.hdr = h;
         if (a.hdr_host) *a.hdr_host = h;
         // the tick is over: every worker CTA has left its loops

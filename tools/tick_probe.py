@@ -51,9 +51,12 @@ def main():
             s._lib.hqs_get_kernel_ms(s._ctx, ms)
             d = dbg(s)
             ghz = d[5] / max(d[6], 1)
+            t_gen = ((d[4] >> 16) & 0xFFFF) * 256 / ghz / 1e3
+            t_pack = ((d[7] >> 8) & 0xFFFFFF) * 256 / ghz / 1e3
             print(f"{tag} n={n} w={w}: assigned {m.n_assigned()} host {dt*1e3:.3f} ms kernel {ms[3]*1e3:.1f} us "
-                  f"[stage+count {d[0]/ghz/1e3:.1f} | compact {d[1]/ghz/1e3:.1f} | solve {d[2]/ghz/1e3:.1f} | emit {d[3]/ghz/1e3:.1f}] us "
-                  f"groups {d[4]} packs {d[7]} clock {ghz:.3f} GHz", flush=True)
+                  f"[stage+count {d[0]/ghz/1e3:.1f} | compact {d[1]/ghz/1e3:.1f} | solve {d[2]/ghz/1e3:.1f} (pack {t_pack:.1f}, general loop {t_gen:.1f}) | "
+                  f"emit {d[3]/ghz/1e3:.1f}] us groups {d[4] & 0xFFFF} visits {d[4] >> 32} packs {d[7] & 0xFF} lean groups {d[7] >> 32} "
+                  f"clock {ghz:.3f} GHz", flush=True)
             s.rearm()
         s.close()
 
