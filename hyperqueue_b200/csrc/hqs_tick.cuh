@@ -25,8 +25,9 @@ constexpr u32 TICK_WARPS = TICK_THREADS / 32;
 constexpr u32 EMIT_ROWS_MAX = 16;     // rows of 32 tasks per emit warp and chunk
 constexpr u32 EMIT_SEG_SMEM = 1024;   // count segments cached in shared memory by the emit step
 constexpr u32 CMD_PACK = 1, CMD_EMIT = 2, CMD_EXIT = 3;      // grid commands: cmd word = (sequence << 2) | type
-constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3, BLK_PREFILL = 4;    // block commands inside the solver CTA
-constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4, TF_NO_REFRESH = 8;   // TF_NO_REFRESH: measuring aid (HQS_DEBUG_NO_REFRESH)
+constexpr u32 BLK_PACK = 1, BLK_RESTART = 2, BLK_END = 3, BLK_PREFILL = 4, BLK_WIDE = 5;    // block commands inside the solver CTA
+constexpr u32 TF_COUNT = 1, TF_EMIT = 2, TF_PACK = 4, TF_NO_REFRESH = 8, TF_NO_WIDE = 16;   // TF_NO_REFRESH / TF_NO_WIDE: measuring aids (HQS_DEBUG_NO_REFRESH, HQS_DEBUG_NO_WIDE)
+constexpr u32 WIDE_MAX_GROUP = 0x03FFFFFFu;   // largest group the wide first-fit handles (32-bit prefix sums)
 constexpr u32 SM_NONE = 0xFFFFFFFFu;
 constexpr u32 PF_SEG_CAP = 1u << 18;  // prefill segments (eligible workers summed over classes) per tick
 constexpr u32 MU_MAX_PASSES = 8;      // restarts of the min-utilisation rule before the remaining violators are dropped
@@ -490,7 +491,12 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     __shared__ u32 s_wcnt[TICK_WARPS];
     __shared__ u32 s_pkpos[PACK_MAX_CAND], s_pknseg[PACK_MAX_CAND], s_pkseglo[PACK_MAX_CAND], s_pkex[PACK_MAX_CAND], s_cbase[PACK_MAX_CAND + 1];
     __shared__ u32 s_blk[8];            // block command: type, li, lj, seg region base, phi (2 words), n_packs
-    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks, s_partial, s_npref;
+    __shared__ u32 s_nlist, s_multi, s_err, s_final_err, s_npacks, s_partial, s_npref, s_bign;
+    __shared__ unsigned long long s_wx[2][TICK_WARPS];   // wide first-fit: one record per warp and group (double-buffered)
+#ifdef HQS_TRACE
+    __shared__ u32 s_trw[8];
+#endif
+    __shared__ u32 s_wc[TICK_WARPS];                     //                 per warp: count segments written for the LAST group
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 W = a.W, Q = a.Q, R = a.R, G = a.G;
     const u32 nW = gridDim.x - 1;
@@ -563,7 +569,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     };
 
     // ---- prologue A: staging (overlaps the histogram of the worker CTAs)
-    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; s_partial = 0; s_npref = 0; }
+    if (tid == 0) { s_nlist = 0; s_multi = 0; s_err = 0; s_final_err = 0; s_npacks = 0; s_partial = 0; s_npref = 0; s_bign = 0; }
     if (tid < HQS_MAX_RESOURCES) { s_totmax[tid] = 0; s_D[tid] = 0; s_C[tid] = 0; }
     if (a.sm.classes != SM_NONE) {
         const uint4* src = reinterpret_cast<const uint4*>(a.classes);
@@ -707,6 +713,7 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
             const u32 c = s_gcl[e] & 0xFFFFu, n = s_glist[e].y;
             const Cls& cl = classes[c];
             if (cl.n_variants > 1) multi = 1;
+            if (n > WIDE_MAX_GROUP) s_bign = 1;
             const Var& dv = cl.v[vorder[c * HQS_MAX_VARIANTS]];
             if (dv.all_mask) multi = 1;
             bool servable = true;
@@ -745,9 +752,178 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
     const long long t_prologue = clock64();
 
     // =============================================================================================
+    // wide lean first-fit (plain ticks without reservations / proactive filling, pools of up to 512 workers): EVERY worker
+    // is a lane.  Warp j holds the free vectors of workers 32 j .. 32 j + 31 in registers for the whole loop, so a group
+    // costs ONE step for the whole pool instead of one step per visited tile of a single warp: fit count per lane, warp
+    // sum, exchange of the warp sums through shared memory (one 8-byte record per warp and group, double-buffered, one
+    // named barrier), prefix over the warps, and only the warps the group reaches scan their lanes and take.  The result
+    // is exactly the first-fit of the one-warp loop (ascending worker id); the class frontiers are not needed.  Count
+    // segments: a warp with takers knows that every warp below it is a full taker, so its segment index is the running
+    // base + the non-zero lanes below it; the number of segments a warp wrote travels in its record of the NEXT group,
+    // so the group record of warp 0 trails by one group.  A class nobody could take a task of is dead for the rest of
+    // the loop (free amounts only shrink here): its later groups are skipped without an exchange.
+    // =============================================================================================
+    struct WideOut { u32 seg_base, out_base, steps; bool overflow; };
+    constexpr int WIDE_WORDS = RT * (int)(sizeof(AT) / 4);                      // registers of one free vector
+    const bool wide_ok = plain && !s_bign && !(a.flags & TF_NO_WIDE) && WIDE_WORDS <= 16 && n_tiles <= TICK_WARPS && a.sm.classes != SM_NONE;
+    auto run_wide = [&]() -> WideOut {
+        const u32 li0 = s_blk[1];
+        u32 out_base = s_blk[2], seg_cur = s_blk[3];
+        const u32 nw = n_tiles;                        // participating warps: one tile of 32 workers each
+        WideOut res;
+        res.seg_base = seg_cur; res.out_base = out_base; res.steps = 0; res.overflow = false;
+        uint8_t* s_dead = s_noresv;                    // [Q], all zero here (reservations are off in this loop)
+        // the class table through a pointer the compiler knows to be shared memory (`classes` is shared-or-global: generic loads)
+        const Cls* cls_s = reinterpret_cast<const Cls*>(smem + a.sm.classes);
+        if (warp < nw) {
+            const u32 lt_mask = (1u << lane) - 1;
+            const u32 wk = warp * 32 + lane;
+            const bool in_pool = wk < W;
+            AT fr[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) fr[r] = in_pool ? s_fr[(size_t)wk * RT + r] : 0;
+            u32 par = 0, cme_prev = 0;
+            bool pend = false;
+#ifdef HQS_TRACE
+            u32 tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TWC() ([] { u32 c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)::"memory"); return c_; }())
+            u32 tw_prev = TWC();
+#define TW(i) { const u32 c__ = TWC(); tw[i] += c__ - tw_prev; tw_prev = c__; }
+#else
+#define TW(i)
+#endif
+            u32 p_g = 0, p_k = 0, p_out = 0, p_seglo = 0;      // warp 0: the record that waits for its segment count
+            uint2 ge_n = s_glist[li0];
+            u32 c_n = s_gcl[li0] & 0xFFFFu;
+            Var dv_n = cls_s[c_n].v[0];
+            u32 dead_n = s_dead[c_n];
+            for (u32 e = li0; e < n_list; ++e) {
+                const uint2 ge = ge_n;
+                const u32 c = c_n;
+                Var dv = dv_n;
+                dv.all_mask = 0;                                   // plain tick: lets the compiler drop the `All` arm
+                const u32 dead = dead_n;
+                if (e + 1 < n_list) {
+                    ge_n = s_glist[e + 1];
+                    c_n = s_gcl[e + 1] & 0xFFFFu;
+                    dv_n = cls_s[c_n].v[0];
+                    dead_n = s_dead[c_n];
+                }
+                if (dead) continue;                                // k stays 0 (prologue)
+                const u32 g = ge.x, n = ge.y;
+                par ^= 1u;
+                TW(0)                                              // loop top: entry, prefetch of the next group
+                // ---- fit count of my lane, warp sum (clamped to n: prefixes stay below 2^32), record out
+                const u32 cnt = in_pool ? (u32)fit_count<RT>(fr, 0u, dv, (u64)n) : 0u;
+                TW(1)                                              // fit count
+                u32 total = __reduce_add_sync(0xffffffffu, cnt);
+                total = total < n ? total : n;
+                const u32 nzm = __ballot_sync(0xffffffffu, cnt != 0);
+                if (lane == 0)       // one 8-byte record: total (27 bits) | non-zero lanes (6) << 27 | my segments of the previous group << 34
+                    s_wx[par][warp] = (unsigned long long)total | ((unsigned long long)__popc(nzm) << 27) | ((unsigned long long)cme_prev << 34);
+                TW(2)                                              // warp sum, vote, record
+                // ---- the other warps' records of this group (double-buffered: one barrier per group is enough)
+                bar_named(3, nw * 32);
+                u32 tj = 0, nzj = 0, cprev = 0;
+                if (lane < nw) {
+                    const unsigned long long v = s_wx[par][lane];
+                    tj = (u32)v & 0x07FFFFFFu; nzj = (u32)(v >> 27) & 0x7Fu; cprev = (u32)(v >> 34) & 0x7Fu;
+                }
+                TW(3)                                              // exchange
+                const u32 base = __reduce_add_sync(0xffffffffu, lane < warp ? tj : 0u);
+                const u32 all = __reduce_add_sync(0xffffffffu, tj);
+                const u32 nzb = __reduce_add_sync(0xffffffffu, lane < warp ? nzj : 0u);
+                const u32 sprev = __reduce_add_sync(0xffffffffu, cprev);
+                // the previous group's segments are counted now: its record (warp 0), my segment base
+                if (warp == 0 && lane == 0 && pend) {
+                    GroupOut go;
+                    go.k = p_k; go.out_off = p_out; go.seg_lo = p_seglo; go.seg_n = sprev;
+                    a.gout[p_g] = go;
+                }
+                seg_cur += sprev;
+                if (seg_cur > SEG_CAP) { res.overflow = true; seg_cur = SEG_CAP; }
+                TW(4)                                              // prefix over the warps, previous record
+                // ---- take: lanes in worker order until n is handed out.  Only a warp that the group reaches scans its lanes.
+                u32 cme = 0;
+                if (base < n && nzm != 0) {
+                    const u32 room = n - base;                     // what the warps below me left
+                    u32 inc = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+                        if ((int)lane >= d) inc += y;
+                    }
+                    const u32 exl = inc - cnt;
+                    TW(5)                                          // scan
+                    u32 take = 0;
+                    if (cnt && exl < room) take = min(cnt, room - exl);
+                    const u32 tkm = __ballot_sync(0xffffffffu, take != 0);
+                    if (take) {
+                        const u32 si = seg_cur + nzb + __popc(tkm & lt_mask);
+                        if (si < SEG_CAP) { a.seg_cum[si] = base + exl + take; a.seg_wv[si] = wk; }
+                    }
+                    // an unused resource has amount 0 (hqs_classes_set), `All` does not occur in a plain tick: branch-free
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) fr[r] = fr[r] == AMAX ? fr[r] : fr[r] - (AT)take * dv.amount[r];
+                    cme = __popc(tkm);
+                }
+                cme_prev = cme;
+                TW(6)                                              // takes, segments
+                const u32 k = all < n ? all : n;
+                if (all == 0) {                                    // nobody can take a task of the class any more
+                    if (lane == 0) s_dead[c] = 1;
+                    if (c_n == c) dead_n = 1;
+                    __syncwarp();
+                }
+                if (warp == 0) {
+                    u32 k_loc = k;
+                    if (before) {
+                        const u32 bef = s_bef ? s_bef[e] : __ldcg(before + g);
+                        const u32 loc = s_loc ? s_loc[e] : __ldcg(a.total_local + g);
+                        k_loc = k > bef ? k - bef : 0;
+                        k_loc = k_loc < loc ? k_loc : loc;
+                    }
+                    p_g = g; p_k = k; p_out = out_base; p_seglo = seg_cur; pend = true;
+                    out_base += k_loc;
+                    ++res.steps;
+                }
+                TW(7)                                              // group record
+            }
+#ifdef HQS_TRACE
+            if (warp == 0 && lane == 0)
+                for (int q = 0; q < 8; ++q) s_trw[q] = tw[q];
+#endif
+            // free vectors back to shared memory
+            if (in_pool) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r) s_fr[(size_t)wk * RT + r] = fr[r];
+            }
+            if (lane == 0) s_wc[warp] = cme_prev;
+            bar_named(2, TICK_THREADS);
+            if (warp == 0) {
+                // the last group's segment count
+                const u32 clast = lane < nw ? s_wc[lane] : 0u;
+                const u32 slast = __reduce_add_sync(0xffffffffu, clast);
+                if (lane == 0 && pend) {
+                    GroupOut go;
+                    go.k = p_k; go.out_off = p_out; go.seg_lo = p_seglo; go.seg_n = slast;
+                    a.gout[p_g] = go;
+                }
+                seg_cur += slast;
+                if (seg_cur > SEG_CAP) { res.overflow = true; seg_cur = SEG_CAP; }
+                res.seg_base = seg_cur; res.out_base = out_base;
+            }
+        } else {
+            bar_named(2, TICK_THREADS);
+        }
+        return res;
+    };
+
+    // =============================================================================================
     // block-parallel steps, executed by ALL warps of the CTA (the solver warp calls block_work after waking the others)
     // =============================================================================================
     auto block_work = [&](u32 cmd) {
+        if (cmd == BLK_WIDE) { run_wide(); return; }
         if (cmd == BLK_RESTART) {
             // min-utilisation restart: excluded workers stay out, everything else starts over
             stage_workers();
@@ -1368,7 +1544,17 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
                             }
                         }
                     };
-                    if (resv_on || s_kk) lean_loop(std::true_type{}); else lean_loop(std::false_type{});
+                    if (resv_on || s_kk) lean_loop(std::true_type{});
+                    else if (wide_ok) {
+                        // every worker a lane: all warps of the CTA (see wide_loop)
+                        if (lane == 0) { s_blk[0] = BLK_WIDE; s_blk[1] = li; s_blk[2] = out_base; s_blk[3] = seg_base; }
+                        __syncwarp();
+                        bar_named(1, TICK_THREADS);
+                        const WideOut wo = run_wide();
+                        seg_base = wo.seg_base; out_base = wo.out_base;
+                        seg_overflow |= wo.overflow;
+                        n_visits += wo.steps;
+                    } else lean_loop(std::false_type{});
                     __syncwarp();
                     n_fast += n_list - li;
                     li = n_list;
@@ -1671,6 +1857,10 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         h.dbg[1] = ((unsigned long long)tr_fit << 32) | tr_load;
         for (int q = 0; q < 4; ++q) h.dbg[2 + q] = ((unsigned long long)tr_n[q] << 32) | tr_cyc[q];
         h.dbg[6] = (unsigned long long)(t_solved - t_prologue);
+        if (n_fast && tr_n[0] + tr_n[1] + tr_n[2] + tr_n[3] == 0) {      // the wide loop ran: its section sums (warp 0)
+            for (int q = 0; q < 4; ++q) h.dbg[q] = ((unsigned long long)s_trw[2 * q + 1] << 32) | s_trw[2 * q];
+            h.dbg[4] = n_visits;
+        }
 #endif
         *a.hdr = h;
         if (a.hdr_host) *a.hdr_host = h;

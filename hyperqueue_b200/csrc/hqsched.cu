@@ -649,7 +649,9 @@ int launch_tick(hqs_ctx* ctx, const TickGeom& t, u32 W, const TickLayout& lay, b
     TickArgs a = base_args(ctx, t, W, lay, blocked);
     a.out_cap = out_cap;
     static const bool no_refresh = getenv("HQS_DEBUG_NO_REFRESH") != nullptr;   // measuring aid: frontiers are not refreshed after a pack
-    a.flags = (d_counts_all ? 0u : TF_COUNT) | (emit ? TF_EMIT : 0u) | (ctx->pack ? TF_PACK : 0u) | (no_refresh ? TF_NO_REFRESH : 0u);
+    static const bool no_wide = getenv("HQS_DEBUG_NO_WIDE") != nullptr;         // measuring aid: plain ticks use the one-warp lean loop
+    a.flags = (d_counts_all ? 0u : TF_COUNT) | (emit ? TF_EMIT : 0u) | (ctx->pack ? TF_PACK : 0u) | (no_refresh ? TF_NO_REFRESH : 0u) |
+              (no_wide ? TF_NO_WIDE : 0u);
     a.total_ext = d_counts_all;
     a.before_ext = d_before;
     if (exchange) {

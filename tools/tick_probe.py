@@ -13,6 +13,9 @@ import greedy_model as G
 import workloads as WL
 from hyperqueue_b200 import _lib as L
 
+if os.environ.get("HQS_LIB"):        # a variant build (tools/variant_build.sh)
+    L.LIB_PATH = os.path.join(ROOT, "hyperqueue_b200", os.environ["HQS_LIB"])
+
 
 def dbg(s):
     d = (C.c_uint64 * 8)()
