@@ -149,6 +149,28 @@ CASES = [
     case([(12,)], [(0, cw(3, weight=1.1))] * 5 + [(0, cw(0, all_cpus=True))], [[cw(3, weight=1.1)] * 4], "weight2-a"),
     case([(12,)], [(0, cw(3))] * 5 + [(0, cw(0, weight=1.1, all_cpus=True))], [[cw(0, weight=1.1, all_cpus=True)]], "weight2-b"),
     # test_schedule_min_utilization3 :1447-1463 is in tests/test_gpu_edges.py (needs worker options)
+    # test_schedule_variants2 :757-784: 10 tasks of {6 cpus} | {2 cpus + 2 gpus} on 12 cpus with 0 / 4 / 20 gpus
+    case([(12, 0)], [(0, cv({0: 6}, {0: 2, 1: 2}))] * 10, "varcounts:2,0", "var2-nogpu", resources=2),
+    case([(12, 4)], [(0, cv({0: 6}, {0: 2, 1: 2}))] * 10, "varcounts:1,2", "var2-4gpus", resources=2),
+    case([(12, 20)], [(0, cv({0: 6}, {0: 2, 1: 2}))] * 10, "varcounts:0,6", "var2-20gpus", resources=2),
+    # test_no_deps_scattering_2 :816-847: one new 1-cpu task per tick on 3 x 5 cpus; the running tasks of the earlier ticks
+    # keep their cpus (the reference compares sorted counts; first-fit fills the lowest worker id)
+    case([(5,), (5,), (5,)], [(0, c(1))], "perworker:1,0,0", "scatter2-a", running={0: 3}),
+    case([(5,), (5,), (5,)], [(0, c(1))], "perworker:0,1,0", "scatter2-b", running={0: 5, 1: 2}),
+    case([(5,), (5,), (5,)], [(0, c(1))], "perworker:0,0,1", "scatter2-c", running={0: 5, 1: 5, 2: 4}),
+    case([(5,), (5,), (5,)], [(0, c(1))], "perworker:0,0,0", "scatter2-d", running={0: 5, 1: 5, 2: 5}),
+    # test_generic_resource_assign2 :906-937: w1 (10 cpus, 10 Res0), w2 (10 cpus), w3 (10 cpus, 10 Res0, 1e6 Res1);
+    # 50 x {1 cpu, 1 Res0} + 50 x {1 cpu, 2 Res0}: 10 tasks of the first kind on w1 and on w3, nothing on w2
+    case([(10, 10, 0), (10, 0, 0), (10, 10, 1000000)], [(0, c(1, r1=1))] * 50 + [(0, c(1, r1=2))] * 50,
+         [[c(1, r1=1)] * 10, [], [c(1, r1=1)] * 10], "gres-assign2", resources=3),
+    # test_generic_resource_balance1/2 :939-990
+    case([(10, 10, 0), (10, 0, 0), (10, 10, 1000000)], [(0, c(1, r1=5))] * 4, "perworker:2,0,2", "gres-balance1", resources=3),
+    case([(10, 10, 0), (10, 0, 0), (10, 10, 1000000)],
+         [(0, c(1, r1=5)), (0, c(1, r1=5, r2=500000)), (0, c(1, r1=5)), (0, c(1, r1=5, r2=500000))],
+         [[c(1, r1=5)] * 2, [], [c(1, r1=5, r2=500000)] * 2], "gres-balance2", resources=3),
+    # test_scheduler_two_running_three_waiting :1110-1127: 8 cpus + 4 foo, two running {1 cpu, 2 foo} tasks hold all foo;
+    # the 2-cpu task at priority 1 is assigned, the two waiting {1 cpu, 2 foo} tasks stay
+    case([(8, 4)], [(1, c(2)), (0, c(1, r1=2)), (0, c(1, r1=2))], [[c(2)]], "two-running-three-waiting", running={0: (2, 4)}, resources=2),
 ]
 
 
@@ -179,8 +201,9 @@ def to_workload(cs) -> Tuple[Workload, List[Tuple]]:
         for r, u in enumerate(res):
             total[w, r] = u * FR
     free = total.copy()
-    for w, used_cpus in cs["running"].items():
-        free[w, 0] -= np.uint64(used_cpus * FR)
+    for w, used in cs["running"].items():          # cpus in use, or units in use per resource
+        for r, u in enumerate(used if isinstance(used, tuple) else (used,)):
+            free[w, r] -= np.uint64(u * FR)
     rem = None
     if cs.get("worker_time"):
         rem = np.full(W, np.inf)
@@ -213,6 +236,10 @@ def check(cs, wl, keys, a) -> Optional[str]:
             return cs["check"](perp)
         if kind == "count":
             return None if a.shape[0] == int(arg) else f"assigned {a.shape[0]} != {arg}"
+        if kind == "varcounts":        # assigned tasks per variant id
+            got = np.bincount(a["variant"], minlength=8).tolist()
+            want = [int(x) for x in arg.split(",")]
+            return None if got[:len(want)] == want and sum(got[len(want):]) == 0 else f"variant counts {got} != {want}"
         if kind == "perworker":
             want = [int(x) for x in arg.split(",")]
             got = [len(p) for p in per]
