@@ -415,8 +415,10 @@ def run_cuda(args) -> dict:
     kernels = {"tick_k": {"ms": float(acc[3]), "phases_ms": {"stage+histogram": float(acc[0]), "exchange+compact+solve": float(acc[1]),
                                                              "emit": float(acc[2])},
                           "groups": st["n_groups"], "segments": st["n_segments"],
-                          "note": "phases as seen by the solver CTA's clock, scaled to the event-timed kernel duration; the solve is one "
-                                  "warp walking the non-empty groups (latency-bound), histogram and emit stream the task table"}}
+                          "note": "phases as seen by the solver CTA's clock, scaled to the event-timed kernel duration; the solve is a "
+                                  "sequential chain over the non-empty groups (pools of up to 512 workers: every worker a lane, one "
+                                  "step per group; larger pools: one warp over tiles of 32 workers), histogram and emit stream the "
+                                  "task table"}}
 
     extra = {}
     # ---- mode M2: zero-duration drains with REAL capacities, every tick through the public call;
