@@ -46,6 +46,15 @@ def test_tick_matches_specification(n, w, q, seed):
     _tick_vs_model(P.make_independent(n, w, q, seed))
 
 
+@pytest.mark.parametrize("n,w,q,seed,scale", [(30000, 33, 8, 11, 1024), (120000, 300, 16, 12, 1024), (150000, 512, 16, 13, 1024),
+                                              (80000, 300, 16, 14, 1), (90000, 512, 12, 15, 1), (40000, 513, 8, 16, 1024)])
+def test_wide_first_fit_pool_shapes(n, w, q, seed, scale):
+    """Plain ticks on pools of up to 512 workers run the wide first-fit (every worker a lane, one warp per 32 workers): ragged
+    last warp (33, 300), all 16 warps (512), every task assignable (scale 1024) and saturated pools (scale 1: pack first, then
+    dead classes are skipped); 513 workers fall back to the one-warp loop.  Bit-exact against the specification."""
+    _tick_vs_model(P.make_independent(n, w, q, seed, free_scale=scale))
+
+
 def test_tick_variants_and_blocked():
     _tick_vs_model(P.make_independent(20000, 32, 12, seed=7, variants3=True, blocked_density=0.05))
 
