@@ -918,6 +918,10 @@ __device__ void solver_cta(const TickArgs& a, unsigned char* smem) {
         }
         return res;
     };
+#undef TW
+#ifdef HQS_TRACE
+#undef TWC
+#endif
 
     // =============================================================================================
     // block-parallel steps, executed by ALL warps of the CTA (the solver warp calls block_work after waking the others)
