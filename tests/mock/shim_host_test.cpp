@@ -77,6 +77,60 @@ int main() {
         try { core.add_ready_task(TaskId{9, 9}, 77, 0); } catch (const std::invalid_argument&) { threw = true; }
         check(threw, "unknown request id is refused");
     }
+    {   // proactive filling, retract + redirect, on_retract_response, RunningPrefilled (mapping.rs:63-101, 156-230, 255-288;
+        // reactor.rs:263-345, 452-498): the shim's bookkeeping of kind 1 / kind 2 records
+        GpuCore core(1, 0);
+        core.set_scheduler_config(0, 10);
+        const ResourceRqId c1 = core.get_or_create_resource_rq_id(cpus(1));
+        core.on_new_worker(1, {2 * FRACTIONS_PER_UNIT});
+        std::vector<TaskId> ids;
+        for (uint32_t k = 1; k <= 4; ++k) ids.push_back(TaskId{3, k});
+        core.on_new_tasks(ids);
+        for (const TaskId& t : ids) core.add_ready_task(t, c1, priority_from_user(0));
+        WorkerTaskMapping m = core.run_scheduling();
+        check(m.workers[1].assigned.size() == 2 && m.workers[1].prefills.size() == 2 && m.workers[1].retracts.empty(),
+              "two tasks run, the other two are prefilled behind them");
+        check(m.workers[1].assigned[0].first == (TaskId{3, 1}) && m.workers[1].prefills[0] == (TaskId{3, 3}), "ascending TaskId inside the class");
+        check(core.n_prefilled(1) == 2 && core.free_resources(1)[0] == 0, "prefilled tasks take no resources");
+        check(core.run_scheduling().workers.empty(), "nothing changes without an event");
+        // a second worker appears: the prefilled tasks are the only ready ones, they move (RetractTasks to worker 1,
+        // redirect to worker 2)
+        core.on_new_worker(2, {2 * FRACTIONS_PER_UNIT});
+        m = core.run_scheduling();
+        check(m.workers.count(1) && m.workers[1].retracts.size() == 2 && m.workers[1].assigned.empty(), "RetractTasks goes to the holder");
+        check(!m.workers.count(2) || m.workers[2].assigned.empty(), "the new worker gets the tasks only after the retract response");
+        check(core.redirects().size() == 2 && core.n_prefilled(1) == 0, "SchedulerState::redirects holds both tasks");
+        check(core.free_resources(2)[0] == 0, "the target's resources are taken at once");
+        auto to = core.on_retract_response(1, {TaskId{3, 3}, TaskId{3, 4}});
+        check(to.size() == 1 && to.count(2) && to[2].size() == 2 && to[2][0].first == (TaskId{3, 3}) && to[2][0].second == 0,
+              "the retract response releases the redirected ComputeTasks");
+        check(core.redirects().empty(), "redirects are consumed");
+        check(core.on_retract_response(1, {TaskId{3, 3}}).empty(), "a second response for the same task is ignored");
+        core.on_task_finished(TaskId{3, 3});
+        check(core.free_resources(2)[0] == 1 * FRACTIONS_PER_UNIT, "a redirected task returns its resources to the target");
+    }
+    {   // RunningPrefilled: the worker starts a prefilled task on its own (reactor.rs:263-345)
+        GpuCore core(1, 0);
+        core.set_scheduler_config(0, 10);
+        const ResourceRqId c1 = core.get_or_create_resource_rq_id(cpus(1));
+        core.on_new_worker(5, {1 * FRACTIONS_PER_UNIT});
+        std::vector<TaskId> ids = {TaskId{4, 1}, TaskId{4, 2}, TaskId{4, 3}};
+        core.on_new_tasks(ids);
+        for (const TaskId& t : ids) core.add_ready_task(t, c1, priority_from_user(0));
+        WorkerTaskMapping m = core.run_scheduling();
+        check(m.workers[5].assigned.size() == 1 && m.workers[5].prefills.size() == 2, "one runs, two are prefilled");
+        const uint32_t removes_before = core.stats().n_segments;
+        core.on_task_finished(TaskId{4, 1});
+        core.on_task_running_prefilled(TaskId{4, 2}, 0);
+        check(core.n_prefilled(5) == 1 && core.free_resources(5)[0] == 0, "the started task holds the cpu, one prefill is left");
+        check(core.stats().n_segments == removes_before + 1, "the started task leaves the device ready set");
+        m = core.run_scheduling();
+        check(m.n_assigned() == 0, "the worker is full: the remaining prefilled task stays where it is");
+        core.on_task_finished(TaskId{4, 2});
+        m = core.run_scheduling();
+        check(m.workers.count(5) && m.workers[5].retracts.size() == 1 && core.redirects().size() == 1,
+              "a prefilled task that is assigned (here to its own holder) goes through retract + redirect like in the reference");
+    }
     std::fprintf(stderr, "shim host test: %d failed\n", failed);
     return failed;
 }

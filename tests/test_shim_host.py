@@ -1,6 +1,7 @@
 """Host logic of the C++ shim (tako_b200::GpuCore) without a GPU: hyperqueue_b200/csrc/tako_shim.cpp is compiled
 against a TEST DOUBLE of the C ABI (tests/mock/fake_hqsched.cpp, a host-memory first-fit) and driven through
-interning, batched pushes, cancellation, applying a tick to the worker mirror, resource return and worker removal.  The real library is exercised by the same shim on the GPU
+interning, batched pushes, cancellation, applying a tick to the worker mirror, resource return, worker removal, and the
+bookkeeping of proactive filling: prefill records, retract + redirect, on_retract_response, RunningPrefilled.  The real library is exercised by the same shim on the GPU
 (tests/test_gpu_edges.py::test_cpp_shim_selftest)."""
 import os
 import subprocess
